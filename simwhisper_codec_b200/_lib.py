@@ -1,0 +1,72 @@
+"""ctypes binding of libswc.so (C ABI declared in include/swc.h).
+
+The library is built in-tree by `make -C simwhisper_codec_b200/csrc` (or `__graft_entry__.build()`).
+There is no fallback: if the shared object is missing, importing a compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libswc.so")
+
+PRECISION = {"fp32": 0, "bf16": 1}
+STAGE = {"mel": 0, "encoder": 1, "downsample": 2, "quantizer": 3, "upsample": 4, "decoder": 5, "vocos": 6,
+         "tokenize": 7, "detokenize": 8, "forward": 9}
+
+_p, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/swc.h declares
+SIGNATURES = {
+    "swc_version": (_i, []),
+    "swc_last_error": (C.c_char_p, []),
+    "swc_model_create": (_i, [C.POINTER(_p), _i]),
+    "swc_model_set_tensor": (_i, [_p, C.c_char_p, _p, _i, C.POINTER(_i64), _i]),
+    "swc_model_pack": (_i, [_p]),
+    "swc_model_packed_numel": (_i64, [_p, C.c_char_p]),
+    "swc_model_get_packed": (_i, [_p, C.c_char_p, _p, _i64]),
+    "swc_model_finalize": (_i, [_p, _i]),
+    "swc_model_destroy": (None, [_p]),
+    "swc_workspace_bytes": (_sz, [_p, _i, _i, _i]),
+    "swc_mel": (_i, [_p, _p, _i64, _i, _p, _i, _p, _p, _p, _sz, _p]),
+    "swc_encoder": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "swc_downsample": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "swc_quantize": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
+    "swc_dequantize": (_i, [_p, _p, _i, _p, _i, _i, _p, _p]),
+    "swc_upsample": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "swc_decoder": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "swc_vocos": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "swc_tokenize": (_i, [_p, _p, _i64, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "swc_detokenize": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "swc_forward": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "swc_test_gemm": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "swc_test_attention": (_i, [_i, _p, _p, _p, _i, _i, _i, _p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+                "(the SimWhisper-Codec B200 path has no Python/CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().swc_last_error().decode(errors="replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {last_error()}")

@@ -1,0 +1,479 @@
+"""Drop-in `AudioCodec` for the reference's `audiocodec/model.py` (ZhangXinWhut/SimWhisper-Codec),
+backed by the sm_100a kernels of libswc.so.
+
+Same constructor (`AudioCodec(generator_params)`), attributes, sub-module names, `state_dict()` key
+schema and inference API as the reference (audiocodec/model.py:15-396):
+`encode / decode / inference_tokenize / inference_detokenize / forward / load_from_checkpoint`.
+The sub-modules hold the parameters and call the C ABI through `NativeCodec`; there is no PyTorch or
+CPU compute path — without a CUDA device (or without the built library) every forward raises.
+
+Differences that are deliberate and documented in DESIGN.md:
+  * `encode()/decode()` flatten all (item x 30-s window) pairs into one batch instead of looping
+    over windows in Python, and never synchronise with the host (lengths are known on the host);
+    results are identical to the reference's windowing (keep-first 20 s, decode pad length T' =
+    batch maximum per window index, reference model.py:275-297, 340-362).
+  * `precision="bf16"` selects the tcgen05 tensor-core path (fp32 residual stream, LayerNorm,
+    softmax, iSTFT); `precision="fp32"` is the parity mode.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import os
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+import yaml
+
+from .. import _lib
+from ..weights import state_dict_schema
+
+_BUFFER_LEAVES = ("positional_embedding", "filter", "window", "dim_base_index", "num_levels")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class NativeCodec:
+    """Owns the swc_model handle and the scratch workspace of one device."""
+
+    def __init__(self, precision: str):
+        self.lib = _lib.load()
+        self.precision = precision
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.swc_model_create(C.byref(self.handle), _lib.PRECISION[precision]), "swc_model_create")
+        self.device: Optional[torch.device] = None
+        self._ws: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                self.lib.swc_model_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:  # pragma: no cover - interpreter teardown
+            pass
+
+    def set_state(self, sd: Dict[str, torch.Tensor]) -> None:
+        for k, v in sd.items():
+            t = v.detach().to("cpu").contiguous()
+            if t.dtype in (torch.int32,):
+                dt = 1
+            else:
+                t = t.to(torch.float32)
+                dt = 0
+            shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+            _lib.check(self.lib.swc_model_set_tensor(self.handle, k.encode(), _ptr(t), dt, shape, t.dim()),
+                       f"swc_model_set_tensor({k})")
+
+    def pack(self) -> None:
+        _lib.check(self.lib.swc_model_pack(self.handle), "swc_model_pack")
+
+    def packed(self, name: str) -> torch.Tensor:
+        n = self.lib.swc_model_packed_numel(self.handle, name.encode())
+        if n < 0:
+            raise KeyError(name)
+        out = torch.empty(n, dtype=torch.float32)
+        _lib.check(self.lib.swc_model_get_packed(self.handle, name.encode(), _ptr(out), n), "swc_model_get_packed")
+        return out
+
+    def finalize(self, device: torch.device) -> None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("SimWhisper-Codec B200 path needs a CUDA device; there is no CPU fallback")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        _lib.check(self.lib.swc_model_finalize(self.handle, idx), "swc_model_finalize")
+        self.device = torch.device("cuda", idx)
+
+    def workspace(self, stage: str, batch: int, frames: int):
+        need = int(self.lib.swc_workspace_bytes(self.handle, _lib.STAGE[stage], batch, frames))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return _ptr(self._ws), C.c_size_t(self._ws.numel())
+
+
+class _Holder(nn.Module):
+    """Plain container that reproduces the reference module tree so state_dict keys line up."""
+
+
+class _Stage(_Holder):
+    def __init__(self, owner: "AudioCodec", name: str):
+        super().__init__()
+        object.__setattr__(self, "_owner", owner)
+        object.__setattr__(self, "_stage", name)
+
+    def _run(self, fn_name: str, stage: str, x: torch.Tensor, lens: torch.Tensor, out_shape, frames: int):
+        owner = self._owner
+        nat = owner._native_for(x.device)
+        x = x.contiguous().to(torch.float32)
+        lens = lens.to(device=x.device, dtype=torch.int64).contiguous()
+        B = x.shape[0]
+        out = torch.empty(out_shape, dtype=torch.float32, device=x.device)
+        out_lens = torch.empty(B, dtype=torch.int64, device=x.device)
+        ws, nws = nat.workspace(stage, B, frames)
+        fn = getattr(nat.lib, fn_name)
+        _lib.check(fn(nat.handle, _ptr(x), _ptr(lens), B, frames, _ptr(out), _ptr(out_lens), ws, nws, _stream()), fn_name)
+        return out, out_lens
+
+
+class OmniAudioEncoder(_Stage):
+    """reference audiocodec/nn/modules.py:236-376 — forward(input_features (B,80,T), input_length)."""
+
+    def forward(self, input_features, input_length, output_hidden_states=False):
+        if output_hidden_states:
+            raise NotImplementedError("output_hidden_states is not part of the codec hot path")
+        B, _, T = input_features.shape
+        return self._run("swc_encoder", "encoder", input_features, input_length, (B, 768, (T + 1) // 2), T)
+
+
+class FrameStackDownConv(_Stage):
+    """reference modules.py:476-553 — forward(x (B,768,T), input_length) -> (B,32,ceil(T/4))."""
+
+    def forward(self, x, input_length):
+        B, _, T = x.shape
+        return self._run("swc_downsample", "downsample", x, input_length, (B, 32, (T + 3) // 4), T)
+
+
+class FrameStackUpConv(_Stage):
+    """reference modules.py:555-634 — forward(z_q (B,32,T'), input_len) -> (B,768,4T')."""
+
+    def forward(self, z_q, input_len=None):
+        B, _, T = z_q.shape
+        if input_len is None:
+            input_len = torch.full((B,), T, dtype=torch.int64, device=z_q.device)
+        return self._run("swc_upsample", "upsample", z_q, input_len, (B, 768, 4 * T), T)
+
+
+class OmniAudioDecoder(_Stage):
+    """reference modules.py:380-474 — forward(hidden_states (B,768,T), input_length) -> (B,80,2T)."""
+
+    def forward(self, hidden_states, input_length):
+        B, _, T = hidden_states.shape
+        return self._run("swc_decoder", "decoder", hidden_states, input_length, (B, 80, 2 * T), T)
+
+
+class Vocos(_Stage):
+    """reference modules.py:1545-1573 — forward(x (B,80,T), input_length) -> (B,1,160T)."""
+
+    def forward(self, x, input_length):
+        B, _, T = x.shape
+        y, lens = self._run("swc_vocos", "vocos", x, input_length, (B, 160 * T), T)
+        return y[:, None, :], lens
+
+
+class GroupFiniteScalarQuantizer(_Stage):
+    """reference audiocodec/nn/quantizer.py:226-317."""
+
+    def forward(self, inputs, input_len):
+        if inputs.size(1) != 32:
+            raise RuntimeError(
+                f"Input dimension {inputs.size(1)} not matching the expected dimension 32, inputs shape {inputs.shape}")
+        nat = self._owner._native_for(inputs.device)
+        x = inputs.contiguous().to(torch.float32)
+        lens = input_len.to(device=x.device, dtype=torch.int64).contiguous()
+        B, _, T = x.shape
+        zq = torch.empty_like(x)
+        codes = torch.empty((8, B, T), dtype=torch.int32, device=x.device)
+        _lib.check(nat.lib.swc_quantize(nat.handle, _ptr(x), _ptr(lens), B, T, _ptr(zq), _ptr(codes), _stream()), "swc_quantize")
+        return zq, codes
+
+    def encode(self, inputs, input_len):
+        return self.forward(inputs, input_len)[1]
+
+    def decode(self, indices, input_len):
+        if indices.dim() != 3 or indices.size(0) != 8:
+            raise ValueError(f"Expected indices of shape (8, B, T), got {tuple(indices.shape)}")
+        nat = self._owner._native_for(indices.device)
+        if indices.dtype not in (torch.int32, torch.int64):
+            indices = indices.to(torch.int64)
+        idx = indices.contiguous()
+        lens = input_len.to(device=idx.device, dtype=torch.int64).contiguous()
+        _, B, T = idx.shape
+        zq = torch.empty((B, 32, T), dtype=torch.float32, device=idx.device)
+        _lib.check(nat.lib.swc_dequantize(nat.handle, _ptr(idx), int(idx.dtype == torch.int64), _ptr(lens), B, T,
+                                          _ptr(zq), _stream()), "swc_dequantize")
+        return zq
+
+
+class MelFeatureExtractor:
+    """reference audiocodec/nn/feature_extractor.py:19-245, computed on the GPU.  Accepts the same
+    list-of-1-D-arrays input and returns {"input_features" (B,80,3000), "attention_mask" (B,3000)}."""
+
+    def __init__(self, owner: "AudioCodec", **kwargs):
+        self._owner = owner
+        self.n_samples = 480000
+        self.nb_max_frames = 3000
+        self.hop_length = 160
+
+    def __call__(self, raw_speech, sampling_rate=None, return_tensors="pt", return_attention_mask=True,
+                 device="cuda", **_):
+        dev = torch.device(device if device != "cpu" else "cuda")
+        wavs = [torch.as_tensor(w, dtype=torch.float32).reshape(-1)[: self.n_samples] for w in raw_speech]
+        B = len(wavs)
+        L = max(1, max(w.numel() for w in wavs))
+        x = torch.zeros(B, L, dtype=torch.float32, device=dev)
+        for i, w in enumerate(wavs):
+            x[i, : w.numel()] = w.to(dev)
+        lens = torch.tensor([w.numel() for w in wavs], dtype=torch.int64, device=dev)
+        mel, mel_lens = self._owner._mel(x, lens)
+        out = {"input_features": mel}
+        if return_attention_mask:
+            out["attention_mask"] = (torch.arange(3000, device=dev)[None, :] < mel_lens[:, None]).to(torch.int32)
+        return out
+
+
+class AudioCodec(nn.Module):
+    def __init__(self, generator_params: dict, precision: str = None, max_batch: int = None):
+        super().__init__()
+        gp = generator_params
+        self.input_sample_rate = gp["input_sample_rate"]
+        self.output_sample_rate = gp["output_sample_rate"]
+        self.max_audio_seconds = 30
+        self.encoder_downsample_rate = gp["encoder_downsample_rate"]
+        self.decoder_upsample_rate = gp["decoder_upsample_rate"]
+        self.num_groups = gp["quantizer"]["num_groups"]
+        self.codebook_dim_per_group = len(gp["quantizer"]["num_levels_per_group"])
+        self._validate(gp)
+        self.precision = precision or os.environ.get("SWC_PRECISION", "fp32")
+        if self.precision not in _lib.PRECISION:
+            raise ValueError(f"precision must be one of {list(_lib.PRECISION)}, got {self.precision}")
+        self.max_batch = int(max_batch or os.environ.get("SWC_MAX_BATCH", 32))
+
+        self.acoustic_encoder = OmniAudioEncoder(self, "encoder")
+        self.downsample = FrameStackDownConv(self, "downsample")
+        self.quantizer = GroupFiniteScalarQuantizer(self, "quantizer")
+        self.upsample = FrameStackUpConv(self, "upsample")
+        self.acoustic_decoder = OmniAudioDecoder(self, "decoder")
+        self.vocos = Vocos(self, "vocos")
+        self.feature_extractor = MelFeatureExtractor(self, **gp["feature_extractor"])
+
+        # parameter / buffer tree with the reference's key schema (zero-filled until load_state_dict)
+        for key, (shape, dtype, _spec) in state_dict_schema(gp).items():
+            parts = key.split(".")
+            mod = self
+            for p in parts[:-1]:
+                if not hasattr(mod, p):
+                    mod.add_module(p, _Holder())
+                mod = getattr(mod, p)
+            t = torch.zeros(shape, dtype=dtype)
+            if parts[-1] in _BUFFER_LEAVES:
+                mod.register_buffer(parts[-1], t)
+            else:
+                mod.register_parameter(parts[-1], nn.Parameter(t, requires_grad=False))
+        self._native: Optional[NativeCodec] = None
+        self._native_version = -1
+        self._version = 0
+
+    # ------------------------------------------------------------------ config / weights
+    @staticmethod
+    def _validate(gp: dict) -> None:
+        enc, dec, dn, up, q, vo, fe = (gp[k] for k in ("acoustic_encoder", "acoustic_decoder", "downsample",
+                                                       "upsample", "quantizer", "vocos", "feature_extractor"))
+        ok = (enc["d_model"] == 768 and dec["d_model"] == 768 and enc["encoder_attention_heads"] == 12
+              and dec["decoder_attention_heads"] == 12 and enc["encoder_ffn_dim"] == 3072
+              and dec["decoder_ffn_dim"] == 3072 and enc["num_mel_bins"] == 80 and enc["stride_size"] == 2
+              and enc["kernel_size"] == 3 and enc.get("is_acoustic", False)
+              and dn["hidden_dim"] == 512 and up["hidden_dim"] == 512 and dn["stack_factor"] == 4
+              and dn["latent_dim"] == 32 and q["num_groups"] == 8 and len(q["num_levels_per_group"]) == 4
+              and abs(q.get("eps", 1e-3) - 1e-3) < 1e-12
+              and vo["dim"] == 512 and vo["intermediate_dim"] == 4096 and vo["n_fft"] == 640
+              and vo["hop_size"] == 160 and vo["padding"] == "same" and vo["input_channels"] == 80
+              and fe["n_fft"] == 400 and fe["hop_length"] == 160 and fe["feature_size"] == 80
+              and fe["sampling_rate"] == 16000 and gp["input_sample_rate"] == 16000)
+        if not ok:
+            raise ValueError("this build is specialised for config/SimWhisperCodec.yaml (768-d, 12 heads, 512-d "
+                             "resamplers, 8x[8,7,6,6] FSQ, Vocos 512/4096, n_fft 640); other shapes have no kernels")
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        r = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self._version += 1
+        return r
+
+    def _native_for(self, device: torch.device) -> NativeCodec:
+        if device.type != "cuda":
+            raise RuntimeError(f"SimWhisper-Codec B200 path runs on CUDA tensors only (got {device}); no CPU fallback")
+        if self._native is None or self._native_version != self._version or self._native.device != torch.device(
+                "cuda", device.index if device.index is not None else torch.cuda.current_device()):
+            nat = NativeCodec(self.precision)
+            nat.set_state(self.state_dict())
+            nat.finalize(device)
+            self._native, self._native_version = nat, self._version
+        return self._native
+
+    def pack_preview(self) -> NativeCodec:
+        """Host-only packing (no GPU needed): used by CPU tests of the weight layout."""
+        nat = NativeCodec(self.precision)
+        nat.set_state(self.state_dict())
+        nat.pack()
+        return nat
+
+    # ------------------------------------------------------------------ stage helpers
+    def _mel(self, x2d: torch.Tensor, lens: torch.Tensor):
+        nat = self._native_for(x2d.device)
+        B = x2d.shape[0]
+        mel = torch.empty((B, 80, 3000), dtype=torch.float32, device=x2d.device)
+        mel_lens = torch.empty(B, dtype=torch.int64, device=x2d.device)
+        ws, nws = nat.workspace("mel", B, 3000)
+        _lib.check(nat.lib.swc_mel(nat.handle, _ptr(x2d), x2d.stride(0), x2d.shape[1], _ptr(lens), B, _ptr(mel),
+                                   _ptr(mel_lens), ws, nws, _stream()), "swc_mel")
+        return mel, mel_lens
+
+    def _tokenize(self, x2d: torch.Tensor, lens: torch.Tensor, want_zq: bool):
+        """x2d (N, L<=480000) fp32 cuda, lens (N,) int64 cuda -> codes (8,N,375) int32, zq, code lens."""
+        nat = self._native_for(x2d.device)
+        N = x2d.shape[0]
+        codes = torch.empty((8, N, 375), dtype=torch.int32, device=x2d.device)
+        zq = torch.empty((N, 32, 375), dtype=torch.float32, device=x2d.device) if want_zq else None
+        clens = torch.empty(N, dtype=torch.int64, device=x2d.device)
+        mb = self.max_batch
+        for s in range(0, N, mb):
+            n = min(mb, N - s)
+            ws, nws = nat.workspace("tokenize", n, 3000)
+            c_part = codes if N <= mb else torch.empty((8, n, 375), dtype=torch.int32, device=x2d.device)
+            z_part = None if zq is None else zq[s:s + n]
+            _lib.check(nat.lib.swc_tokenize(nat.handle, _ptr(x2d[s:s + n]), x2d.stride(0), x2d.shape[1], _ptr(lens[s:s + n]),
+                                            n, _ptr(c_part), _ptr(z_part), _ptr(clens[s:s + n]), ws, nws, _stream()),
+                       "swc_tokenize")
+            if N > mb:
+                codes[:, s:s + n] = c_part
+        return codes, zq, clens
+
+    def _detokenize(self, codes: torch.Tensor, lens: torch.Tensor):
+        """codes (8,N,T') int32/int64 cuda -> wav (N, 1280 T'), out lens."""
+        nat = self._native_for(codes.device)
+        _, N, Tc = codes.shape
+        wav = torch.empty((N, 1280 * Tc), dtype=torch.float32, device=codes.device)
+        olens = torch.empty(N, dtype=torch.int64, device=codes.device)
+        mb = self.max_batch
+        for s in range(0, N, mb):
+            n = min(mb, N - s)
+            ws, nws = nat.workspace("detokenize", n, Tc)
+            c_part = codes if N <= mb else codes[:, s:s + n].contiguous()
+            _lib.check(nat.lib.swc_detokenize(nat.handle, _ptr(c_part), int(codes.dtype == torch.int64), _ptr(lens[s:s + n]), n,
+                                              Tc, _ptr(wav[s:s + n]), _ptr(olens[s:s + n]), ws, nws, _stream()),
+                       "swc_detokenize")
+        return wav, olens
+
+    # ------------------------------------------------------------------ reference API
+    @torch.inference_mode()
+    def forward(self, batch):
+        """reference model.py:112-165 — {'mel_features' (B,80,T), 'mel_lens' (B,)} -> reconstructed audio."""
+        mel = batch["mel_features"].contiguous().to(torch.float32)
+        lens = batch["mel_lens"].to(device=mel.device, dtype=torch.int64).contiguous()
+        nat = self._native_for(mel.device)
+        B, _, Tm = mel.shape
+        Tc = ((Tm + 1) // 2 + 3) // 4
+        wav = torch.empty((B, 1280 * Tc), dtype=torch.float32, device=mel.device)
+        olens = torch.empty(B, dtype=torch.int64, device=mel.device)
+        ws, nws = nat.workspace("forward", B, Tm)
+        _lib.check(nat.lib.swc_forward(nat.handle, _ptr(mel), _ptr(lens), B, Tm, _ptr(wav), _ptr(olens), _ptr(None),
+                                       ws, nws, _stream()), "swc_forward")
+        return {"reconstructed_audio": wav[:, None, :], "audio_lengths": olens}
+
+    @torch.inference_mode()
+    def inference_tokenize(self, x, input_lengths):
+        """reference model.py:167-210 — x (B,1,T<=30 s) -> zq (B,32,375), codes (8,B,375), codes_lengths."""
+        x2d = x.reshape(x.shape[0], -1).contiguous().to(torch.float32)
+        lens = input_lengths.to(device=x2d.device, dtype=torch.int64).contiguous()
+        codes, zq, clens = self._tokenize(x2d, lens, want_zq=True)
+        return {"zq": zq, "codes": codes, "codes_lengths": clens}
+
+    @torch.inference_mode()
+    def inference_detokenize(self, codes, codes_lengths):
+        """reference model.py:212-242 — codes (8,B,T') -> y (B,1,1280 T'), output_length."""
+        if codes.dtype not in (torch.int32, torch.int64):
+            codes = codes.to(torch.int64)
+        codes = codes.contiguous()
+        lens = codes_lengths.to(device=codes.device, dtype=torch.int64).contiguous()
+        wav, olens = self._detokenize(codes, lens)
+        return {"y": wav[:, None, :], "output_length": olens}
+
+    @torch.inference_mode()
+    def encode(self, wav_list, overlap_seconds=10, device=torch.device("cuda")):
+        """reference model.py:244-308: 30-s windows every (30-overlap) s, first (30-overlap) s of codes kept."""
+        device = torch.device(device)
+        sr, rate = self.input_sample_rate, self.encoder_downsample_rate
+        win = int(self.max_audio_seconds * sr)
+        hop = int((self.max_audio_seconds - overlap_seconds) * sr)
+        keep = hop // rate
+        B = len(wav_list)
+        lens = [int(len(w)) for w in wav_list]
+        jobs = []                                           # (item, start, n_valid)
+        for i, L in enumerate(lens):
+            for c in range((L + hop - 1) // hop if hop > 0 else 0):
+                jobs.append((i, c * hop, min(L - c * hop, win)))
+        if not jobs:
+            return {"codes_list": [torch.zeros(self.num_groups, 0, device=device, dtype=torch.long) for _ in range(B)]}
+        N = len(jobs)
+        width = max(n for _, _, n in jobs)
+        x = torch.zeros((N, width), dtype=torch.float32, device=device)
+        for j, (i, s, n) in enumerate(jobs):
+            x[j, :n] = wav_list[i][s:s + n].to(device=device, dtype=torch.float32, non_blocking=True)
+        wl = torch.tensor([n for _, _, n in jobs], dtype=torch.int64).to(device, non_blocking=True)
+        codes, _, _ = self._tokenize(x, wl, want_zq=False)                     # (8, N, 375)
+        # stitch with one gather: output position p of item i <- window (i, p // keep), frame p % keep
+        src, splits = [], []
+        first_job = {}
+        for j, (i, s, n) in enumerate(jobs):
+            first_job.setdefault(i, j)
+        for i, L in enumerate(lens):
+            n_codes = L // rate
+            splits.append(n_codes)
+            if n_codes:
+                p = torch.arange(n_codes, dtype=torch.int64)
+                src.append((first_job[i] + p // keep) * 375 + p % keep)
+        flat = codes.reshape(self.num_groups, N * 375)
+        if src:
+            out = flat.index_select(1, torch.cat(src).to(device, non_blocking=True))
+        else:
+            out = flat[:, :0]
+        return {"codes_list": list(torch.split(out, splits, dim=1))}
+
+    @torch.inference_mode()
+    def decode(self, codes_list, overlap_seconds=10, device=torch.device("cuda")):
+        """reference model.py:310-373: windows of <=375 codes every 250; the pad length T' of window index c
+        is the batch maximum min(375, maxlen-250c), exactly as the reference's un-padded decode batches."""
+        device = torch.device(device)
+        sr, rate = self.input_sample_rate, self.encoder_downsample_rate
+        win = int(self.max_audio_seconds * sr // rate)
+        keep = int((self.max_audio_seconds - overlap_seconds) * sr // rate)
+        up = self.decoder_upsample_rate
+        B = len(codes_list)
+        lens = [int(c.shape[-1]) for c in codes_list]
+        maxlen = max(lens) if lens else 0
+        outs = [torch.empty(L * up, dtype=torch.float32, device=device) for L in lens]
+        n_chunks = (maxlen + keep - 1) // keep if keep > 0 else 0
+        groups: Dict[int, list] = {}                         # T' -> [(item, chunk, n_valid)]
+        for c in range(n_chunks):
+            Tp = min(c * keep + win, maxlen) - c * keep
+            for i, L in enumerate(lens):
+                n = min(max(L - c * keep, 0), Tp)
+                if n > 0:
+                    groups.setdefault(Tp, []).append((i, c, n))
+        for Tp, jobs in groups.items():
+            N = len(jobs)
+            ct = torch.zeros((self.num_groups, N, Tp), dtype=torch.int64, device=device)
+            for j, (i, c, n) in enumerate(jobs):
+                ct[:, j, :n] = codes_list[i][:, c * keep:c * keep + n].to(device=device, dtype=torch.int64, non_blocking=True)
+            cl = torch.tensor([n for _, _, n in jobs], dtype=torch.int64).to(device, non_blocking=True)
+            wav, _ = self._detokenize(ct, cl)
+            for j, (i, c, n) in enumerate(jobs):
+                m = min(n, keep) * up
+                outs[i][c * keep * up:c * keep * up + m] = wav[j, :m]
+        return {"syn_wav_list": outs}
+
+    @classmethod
+    def load_from_checkpoint(cls, config_path: str, ckpt_path: str, **kwargs):
+        """reference model.py:375-396 — YAML + checkpoint ({'model': sd} or bare state dict), strict."""
+        logging.info(f"Loading model from {config_path} and {ckpt_path}")
+        with open(config_path, "r") as f:
+            config = yaml.safe_load(f)
+        model = cls(config["generator_params"], **kwargs)
+        checkpoint = torch.load(ckpt_path, map_location="cpu")
+        model.load_state_dict(checkpoint["model"] if "model" in checkpoint else checkpoint, strict=True)
+        return model

@@ -1,0 +1,190 @@
+// Problem descriptor shared by the two GEMM back ends (fp32 SIMT and bf16 tcgen05) and the fused
+// epilogues.  Every dense contraction of the codec is expressed as
+//
+//     D[b, m, n] = sum_{tap} sum_{k < tap_k} A[b, m + tap_row[tap], tap_col[tap] + k] * W[n, tap*tap_k + k]
+//
+// with A a channel-last activation (rows outside [0, a_rows) read as zero) — i.e. an implicit-GEMM
+// 1-D convolution whose im2col is only a table of (row shift, column offset) per tap.  Plain linear
+// layers are the 1-tap case.
+#pragma once
+#include "common.cuh"
+
+namespace swc {
+
+enum EpiKind { EPI_STORE = 0, EPI_POWER = 1, EPI_LOGMEL = 2, EPI_FSQ = 3, EPI_HEAD = 4 };
+
+constexpr int kMaxTaps = 8;
+
+struct FsqConst {        // per-dimension constants of one 4-dim FSQ group (reference quantizer.py:129-179)
+  float scale[4];        // (L-1)/2 * (1-eps)
+  float offset[4];       // 0.5 for even L else 0
+  float shift[4];        // tan(offset/scale)
+  float half[4];         // L // 2
+  int base[4];           // mixed-radix base
+  int levels[4];
+};
+
+struct EpiParams {
+  // EPI_STORE: out = (act(acc + bias)) * gamma + residual
+  const float* bias;        // [N] or null
+  const float* gamma;       // [N] or null
+  const float* residual;    // fp32, may alias out
+  long long res_row_stride, res_batch_stride;
+  int act;                  // 0 none, 1 exact GELU
+  void* out;                // TO
+  long long out_row_stride, out_batch_stride;
+  int out_row_mul, out_row_off;   // output row = m * mul + off (deconv parity interleave)
+  bf16* out2;               // optional second bf16 copy with the same addressing (bf16 mode)
+  // EPI_LOGMEL
+  float* item_max;          // [nb], initialised to -inf
+  // EPI_FSQ (N == 32)
+  const long long* lens;    // [nb] valid code frames
+  int nb;                   // batches (codes are laid out (G, nb, m_rows))
+  int* codes;               // (G, nb, m_rows) int32 or null
+  float* zq_cf;             // (nb, 32, m_rows) fp32 channels-first or null
+  float* latent_cf;         // (nb, 32, m_rows) fp32 channels-first or null (pre-quantisation)
+  float* zq_cl;             // (nb, m_rows, 32) fp32 channel-last or null (feeds the up-sampler)
+  FsqConst fsq;
+};
+
+struct GemmDesc {
+  const void* A;            // TA
+  long long a_row_stride;   // elements
+  long long a_batch_stride; // elements
+  int a_rows;               // valid rows per batch
+  int a_cols;               // logical row width (for the tensor map)
+  int m_rows;               // output rows per batch
+  int nb;                   // batches
+  int n_taps;
+  int tap_row[kMaxTaps];
+  int tap_col[kMaxTaps];
+  int tap_k;                // multiple of 16 (SIMT) / 64 (tcgen05)
+  const void* W;            // [N_pad, K] row-major, K = n_taps * tap_k
+  int N;                    // logical output columns
+  int w_rows;               // rows present in W (>= N)
+  EpiParams epi;
+};
+
+// ------------------------------------------------------------------------------------------------
+// FSQ on 4 consecutive latent channels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fsq_quantize4(const FsqConst& c, const float* x, float* dq) {
+  int idx = 0;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    float comp = c.scale[d] * tanhf(x[d] + c.shift[d]) - c.offset[d];
+    float r = rintf(comp);                       // ties-to-even like torch.round
+    dq[d] = r / c.half[d];
+    idx += (int)(r + c.half[d]) * c.base[d];
+  }
+  return idx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue on 8 consecutive columns [n0, n0+8) of row m of batch b
+// ------------------------------------------------------------------------------------------------
+template <int KIND, typename TO>
+__device__ __forceinline__ void epi_apply(const EpiParams& p, int b, int m, int n0, int N, int m_rows,
+                                          float (&v)[8]) {
+  if constexpr (KIND == EPI_STORE) {
+    const bool full = (n0 + 8 <= N);
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (full || n0 + j < N) v[j] += __ldg(p.bias + n0 + j);
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+    }
+    if (p.gamma) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (full || n0 + j < N) v[j] *= __ldg(p.gamma + n0 + j);
+    }
+    const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
+    if (p.residual) {
+      const float* r = p.residual + (long long)b * p.res_batch_stride + orow * p.res_row_stride + n0;
+      if (full) {
+        float rv[8];
+        load8(r, rv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += rv[j];
+      } else {
+        for (int j = 0; j < 8; ++j) if (n0 + j < N) v[j] += r[j];
+      }
+    }
+    const long long off = (long long)b * p.out_batch_stride + orow * p.out_row_stride + n0;
+    TO* o = reinterpret_cast<TO*>(p.out) + off;
+    if (full) {
+      store8(o, v);
+      if (p.out2) store8(p.out2 + off, v);
+    } else {
+      for (int j = 0; j < 8; ++j) if (n0 + j < N) {
+        o[j] = from_f32<TO>(v[j]);
+        if (p.out2) p.out2[off + j] = __float2bfloat16_rn(v[j]);
+      }
+    }
+  } else if constexpr (KIND == EPI_POWER) {
+    // columns are interleaved (Re_k, Im_k); write |X_k|^2 to column k (fp32)
+    float* o = reinterpret_cast<float*>(p.out) + (long long)b * p.out_batch_stride + (long long)m * p.out_row_stride;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + 2 * j;
+      if (n + 1 < N) o[n >> 1] = v[2 * j] * v[2 * j] + v[2 * j + 1] * v[2 * j + 1];
+    }
+  } else if constexpr (KIND == EPI_LOGMEL) {
+    float* o = reinterpret_cast<float*>(p.out) + (long long)b * p.out_batch_stride + (long long)m * p.out_row_stride + n0;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (n0 + j < N) {
+        float l = log10f(fmaxf(v[j], 1e-10f));
+        o[j] = l;
+        mx = fmaxf(mx, l);
+      }
+    }
+    if (mx > -INFINITY) atomic_max_float(p.item_max + b, mx);
+  } else if constexpr (KIND == EPI_FSQ) {
+    // two FSQ groups per 8 columns
+    const bool valid = (long long)m < p.lens[b];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int g = (n0 >> 2) + h;
+      float x[4], dq[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) x[d] = v[4 * h + d] + (p.bias ? __ldg(p.bias + n0 + 4 * h + d) : 0.0f);
+      int idx = fsq_quantize4(p.fsq, x, dq);
+      if (!valid) { idx = 0; dq[0] = dq[1] = dq[2] = dq[3] = 0.0f; }
+      if (p.codes) p.codes[((long long)g * p.nb + b) * m_rows + m] = idx;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int c = n0 + 4 * h + d;
+        const long long cf = ((long long)b * 32 + c) * m_rows + m;
+        if (p.zq_cf) p.zq_cf[cf] = dq[d];
+        if (p.latent_cf) p.latent_cf[cf] = x[d];
+        if (p.zq_cl) p.zq_cl[((long long)b * m_rows + m) * 32 + c] = dq[d];
+      }
+    }
+  } else if constexpr (KIND == EPI_HEAD) {
+    // columns interleaved (log-magnitude_k, phase_k) -> S_k = min(exp(mag),100) * (cos p, sin p), fp32
+    float* o = reinterpret_cast<float*>(p.out) + (long long)b * p.out_batch_stride + (long long)m * p.out_row_stride + n0;
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lm = v[2 * j], ph = v[2 * j + 1];
+      if (p.bias && n0 + 2 * j + 1 < N) { lm += __ldg(p.bias + n0 + 2 * j); ph += __ldg(p.bias + n0 + 2 * j + 1); }
+      float mag = fminf(expf(lm), 100.0f);
+      float s, c;
+      sincosf(ph, &s, &c);
+      r[2 * j] = mag * c;
+      r[2 * j + 1] = mag * s;
+    }
+    store8(o, r);   // the S buffer is padded to a multiple of 8 columns; pad columns meet zero iDFT rows
+  }
+}
+
+// launchers ----------------------------------------------------------------------------------------
+// type codes: 0 = fp32, 1 = bf16
+int gemm_simt(const GemmDesc& d, int kind, int a_type, int out_type, cudaStream_t s);
+int gemm_tc(const GemmDesc& d, int kind, int out_type, int num_sms, cudaStream_t s);
+
+}  // namespace swc

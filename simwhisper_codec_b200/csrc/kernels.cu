@@ -1,0 +1,464 @@
+// Bandwidth-bound stages of the codec: LayerNorm, depthwise-conv+LayerNorm, anti-aliased Snake,
+// FSQ, layout conversion, log-mel pre/post passes, iSTFT overlap-add.  All are HBM-streaming
+// kernels: coalesced along the channel (contiguous) dimension, 16/32-byte vector accesses, fp32 math.
+#include "kernels.cuh"
+
+namespace swc {
+
+// ================================================================================================
+// LayerNorm: one warp per row; each lane owns NCH chunks of 8 contiguous channels.
+// ================================================================================================
+template <typename TI, typename TO, int NCH>
+__global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ in, TO* __restrict__ out,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, int nb,
+                                                        int t_in, int t_out, const long long* __restrict__ lens) {
+  constexpr int C = NCH * 256;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)nb * t_out) return;
+  const int b = (int)(row / t_out), t = (int)(row % t_out);
+  TO* o = out + row * C;
+  bool live = t < t_in;
+  if (live && lens) live = (long long)t < lens[b];
+  if (!live) {
+    float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) store8(o + (c * 32 + lane) * 8, z);
+    return;
+  }
+  const TI* x = in + ((long long)b * t_in + t) * C;
+  float v[NCH][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    load8(x + (c * 32 + lane) * 8, v[c]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += v[c][j];
+  }
+  const float mean = warp_sum(sum) * (1.0f / C);
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { float dlt = v[c][j] - mean; sq = fmaf(dlt, dlt, sq); }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / C) + eps);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int c0 = (c * 32 + lane) * 8;
+    float g[8], bt[8], r[8];
+    load8(gamma + c0, g);
+    load8(beta + c0, bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = (v[c][j] - mean) * rstd * g[j] + bt[j];
+    store8(o + c0, r);
+  }
+}
+
+template <typename TI, typename TO>
+static int layernorm_t(const void* in, void* out, const float* g, const float* b, float eps, int nb, int t_in,
+                       int t_out, int C, const long long* lens, cudaStream_t s) {
+  const long long rows = (long long)nb * t_out;
+  const int warps = 8;
+  dim3 grid((unsigned)ceil_div_ll(rows, warps));
+  if (C == 768) layernorm_kernel<TI, TO, 3><<<grid, warps * 32, 0, s>>>((const TI*)in, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
+  else if (C == 512) layernorm_kernel<TI, TO, 2><<<grid, warps * 32, 0, s>>>((const TI*)in, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
+  else if (C == 256) layernorm_kernel<TI, TO, 1><<<grid, warps * 32, 0, s>>>((const TI*)in, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
+  else if (C == 1024) layernorm_kernel<TI, TO, 4><<<grid, warps * 32, 0, s>>>((const TI*)in, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
+  else { set_error("layernorm: unsupported width %d", C); return -1; }
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int layernorm(const void* in, int in_type, void* out, int out_type, const float* gamma, const float* beta,
+              float eps, int nb, int t_in, int t_out, int C, const long long* lens, cudaStream_t s) {
+  if (in_type == 0 && out_type == 0) return layernorm_t<float, float>(in, out, gamma, beta, eps, nb, t_in, t_out, C, lens, s);
+  if (in_type == 0 && out_type == 1) return layernorm_t<float, bf16>(in, out, gamma, beta, eps, nb, t_in, t_out, C, lens, s);
+  set_error("layernorm: unsupported types %d->%d", in_type, out_type);
+  return -1;
+}
+
+// ================================================================================================
+// depthwise conv k7 + bias + LayerNorm (Vocos ConvNeXt block, reference modules.py:1232-1240)
+// ================================================================================================
+template <typename TO, int NCH>
+__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps,
+                                                         TO* __restrict__ out, int nb, int T) {
+  constexpr int C = NCH * 256;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)nb * T) return;
+  const int b = (int)(row / T), t = (int)(row % T);
+  float v[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) load8(bias + (c * 32 + lane) * 8, v[c]);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int tt = t + k - 3;
+    if (tt < 0 || tt >= T) continue;
+    const float* xr = x + ((long long)b * T + tt) * C;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int c0 = (c * 32 + lane) * 8;
+      float xv[8], wv[8];
+      load8(xr + c0, xv);
+      load8(w + k * C + c0, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c][j] = fmaf(xv[j], wv[j], v[c][j]);
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += v[c][j];
+  const float mean = warp_sum(sum) * (1.0f / C);
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { float dlt = v[c][j] - mean; sq = fmaf(dlt, dlt, sq); }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / C) + eps);
+  TO* o = out + row * C;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int c0 = (c * 32 + lane) * 8;
+    float g[8], bt[8], r[8];
+    load8(gamma + c0, g);
+    load8(beta + c0, bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = (v[c][j] - mean) * rstd * g[j] + bt[j];
+    store8(o + c0, r);
+  }
+}
+
+int dwconv7_ln(const float* x, const float* w7c, const float* bias, const float* gamma, const float* beta,
+               float eps, void* out, int out_type, int nb, int T, int C, cudaStream_t s) {
+  SWC_REQUIRE(C == 512, "dwconv7_ln: only C=512 is built (got %d)", C);
+  const long long rows = (long long)nb * T;
+  dim3 grid((unsigned)ceil_div_ll(rows, 8));
+  if (out_type == 0) dwconv7_ln_kernel<float, 2><<<grid, 256, 0, s>>>(x, w7c, bias, gamma, beta, eps, (float*)out, nb, T);
+  else dwconv7_ln_kernel<bf16, 2><<<grid, 256, 0, s>>>(x, w7c, bias, gamma, beta, eps, (bf16*)out, nb, T);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================
+// anti-aliased SnakeBeta (reference alias_free_torch/act.py:23-27, resample.py:25-33, filter.py:83-92,
+// activations.py:107-119; closed form in SURVEY.md appendix A4)
+//   u[2q]   = 2 * sum_a x[cl(q-3+a)] f[11-2a]      u[2q+1] = 2 * sum_a x[cl(q-2+a)] f[10-2a]   a=0..5
+//   v[m]    = u[m] + sin^2(u[m] e^alpha) / (e^beta + 1e-9)
+//   y[t]    = sum_{k<12} v[cl2(2t+k-5)] f[k]
+// one thread = one channel, walking TCH consecutive frames with a 12-deep sliding window of v.
+// ================================================================================================
+constexpr int kSnakeChunk = 32;
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(128) aa_snake_kernel(const TI* __restrict__ in, TO* __restrict__ out,
+                                                       const float* __restrict__ taps_up,
+                                                       const float* __restrict__ taps_dn,
+                                                       const float* __restrict__ alpha_log,
+                                                       const float* __restrict__ beta_log, int T, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.y * kSnakeChunk;
+  if (c >= C) return;
+  float f[12], fd[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { f[i] = __ldg(taps_up + i); fd[i] = __ldg(taps_dn + i); }
+  const float ea = expf(alpha_log[c]);
+  const float inv_b = 1.0f / (expf(beta_log[c]) + 1e-9f);
+  const TI* x = in + (long long)b * T * C + c;
+  TO* y = out + (long long)b * T * C + c;
+  const int T2 = 2 * T;
+
+  auto calc_v = [&](int m) -> float {
+    m = min(max(m, 0), T2 - 1);
+    const int q = m >> 1, odd = m & 1;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      int j = min(max(q - 3 + odd + a, 0), T - 1);
+      float xv = to_f32<TI>(x[(long long)j * C]);
+      float tap = odd ? f[10 - 2 * a] : f[11 - 2 * a];
+      acc = fmaf(xv, tap, acc);
+    }
+    const float u = 2.0f * acc;
+    const float sn = sinf(u * ea);
+    return u + inv_b * (sn * sn);
+  };
+
+  float vw[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) vw[k] = calc_v(2 * t0 + k - 5);
+  const int t1 = min(t0 + kSnakeChunk, T);
+  for (int t = t0; t < t1; ++t) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc = fmaf(vw[k], fd[k], acc);
+    y[(long long)t * C] = from_f32<TO>(acc);
+    if (t + 1 < t1) {
+#pragma unroll
+      for (int k = 0; k < 10; ++k) vw[k] = vw[k + 2];
+      vw[10] = calc_v(2 * (t + 1) + 5);
+      vw[11] = calc_v(2 * (t + 1) + 6);
+    }
+  }
+}
+
+int aa_snake(const void* in, int in_type, void* out, int out_type, const float* taps_up, const float* taps_dn,
+             const float* alpha_log, const float* beta_log, int nb, int T, int C, cudaStream_t s) {
+  dim3 grid(ceil_div(C, 128), ceil_div(T, kSnakeChunk), nb);
+  if (in_type == 0 && out_type == 0) aa_snake_kernel<float, float><<<grid, 128, 0, s>>>((const float*)in, (float*)out, taps_up, taps_dn, alpha_log, beta_log, T, C);
+  else if (in_type == 0 && out_type == 1) aa_snake_kernel<float, bf16><<<grid, 128, 0, s>>>((const float*)in, (bf16*)out, taps_up, taps_dn, alpha_log, beta_log, T, C);
+  else if (in_type == 1 && out_type == 1) aa_snake_kernel<bf16, bf16><<<grid, 128, 0, s>>>((const bf16*)in, (bf16*)out, taps_up, taps_dn, alpha_log, beta_log, T, C);
+  else { set_error("aa_snake: unsupported types %d->%d", in_type, out_type); return -1; }
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================
+// FSQ stand-alone kernels (reference quantizer.py:181-224, 273-317)
+// ================================================================================================
+__global__ void fsq_encode_cf_kernel(const float* __restrict__ z, const long long* __restrict__ lens, int nb, int T,
+                                     FsqConst c, float* zq_cf, int* codes, float* zq_cl) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over (g, b, t)
+  const long long total = 8LL * nb * T;
+  if (i >= total) return;
+  const int t = (int)(i % T);
+  const int b = (int)((i / T) % nb);
+  const int g = (int)(i / ((long long)T * nb));
+  float x[4], dq[4];
+#pragma unroll
+  for (int d = 0; d < 4; ++d) x[d] = z[((long long)b * 32 + g * 4 + d) * T + t];
+  int idx = fsq_quantize4(c, x, dq);
+  if ((long long)t >= lens[b]) { idx = 0; dq[0] = dq[1] = dq[2] = dq[3] = 0.f; }
+  if (codes) codes[i] = idx;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    if (zq_cf) zq_cf[((long long)b * 32 + g * 4 + d) * T + t] = dq[d];
+    if (zq_cl) zq_cl[((long long)b * T + t) * 32 + g * 4 + d] = dq[d];
+  }
+}
+
+int fsq_encode_cf(const float* latent_cf, const long long* lens, int nb, int T, const FsqConst& c, float* zq_cf,
+                  int* codes, float* zq_cl, cudaStream_t s) {
+  const long long total = 8LL * nb * T;
+  fsq_encode_cf_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, s>>>(latent_cf, lens, nb, T, c, zq_cf, codes, zq_cl);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename TI>
+__global__ void fsq_decode_kernel(const TI* __restrict__ codes, const long long* __restrict__ lens, int nb, int T,
+                                  FsqConst c, float* zq_cf, float* zq_cl) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = 8LL * nb * T;
+  if (i >= total) return;
+  const int t = (int)(i % T);
+  const int b = (int)((i / T) % nb);
+  const int g = (int)(i / ((long long)T * nb));
+  const long long idx = (long long)codes[i];
+  const bool valid = (long long)t < lens[b];
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    // python floor-div/mod semantics coincide with C for the non-negative indices of a codebook
+    const long long lvl = (idx / c.base[d]) % c.levels[d];
+    float dq = ((float)lvl - c.half[d]) / c.half[d];
+    if (!valid) dq = 0.f;
+    if (zq_cf) zq_cf[((long long)b * 32 + g * 4 + d) * T + t] = dq;
+    if (zq_cl) zq_cl[((long long)b * T + t) * 32 + g * 4 + d] = dq;
+  }
+}
+
+int fsq_decode(const void* codes, int codes_i64, const long long* lens, int nb, int T, const FsqConst& c,
+               float* zq_cf, float* zq_cl, cudaStream_t s) {
+  const long long total = 8LL * nb * T;
+  const unsigned grid = (unsigned)ceil_div_ll(total, 256);
+  if (codes_i64) fsq_decode_kernel<long long><<<grid, 256, 0, s>>>((const long long*)codes, lens, nb, T, c, zq_cf, zq_cl);
+  else fsq_decode_kernel<int><<<grid, 256, 0, s>>>((const int*)codes, lens, nb, T, c, zq_cf, zq_cl);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================
+// layout conversion through a 32x33 shared tile
+// ================================================================================================
+template <typename TO>
+__global__ void cf_to_cl_kernel(const float* __restrict__ in, TO* __restrict__ out, int C, int T, int t_rows, int c_pitch) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    tile[i][tx] = (c < C && t < T) ? in[((long long)b * C + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    if (t < t_rows && c < c_pitch) out[((long long)b * t_rows + t) * c_pitch + c] = from_f32<TO>(tile[tx][i]);
+  }
+}
+
+int cf_to_cl(const float* in, void* out, int out_type, int nb, int C, int T, int t_rows, int c_pitch, cudaStream_t s) {
+  dim3 grid(ceil_div(t_rows, 32), ceil_div(c_pitch, 32), nb), block(32, 8);
+  if (out_type == 0) cf_to_cl_kernel<float><<<grid, block, 0, s>>>(in, (float*)out, C, T, t_rows, c_pitch);
+  else cf_to_cl_kernel<bf16><<<grid, block, 0, s>>>(in, (bf16*)out, C, T, t_rows, c_pitch);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename TI>
+__global__ void cl_to_cf_kernel(const TI* __restrict__ in, float* __restrict__ out, int C, int T,
+                                long long in_batch_stride, int c_pitch) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    tile[i][tx] = (t < T && c < C) ? to_f32<TI>(in[(long long)b * in_batch_stride + (long long)t * c_pitch + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    if (c < C && t < T) out[((long long)b * C + c) * T + t] = tile[tx][i];
+  }
+}
+
+int cl_to_cf(const void* in, int in_type, float* out, int nb, int C, int T, long long in_batch_stride, int c_pitch, cudaStream_t s) {
+  dim3 grid(ceil_div(T, 32), ceil_div(C, 32), nb), block(32, 8);
+  if (in_type == 0) cl_to_cf_kernel<float><<<grid, block, 0, s>>>((const float*)in, out, C, T, in_batch_stride, c_pitch);
+  else cl_to_cf_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)in, out, C, T, in_batch_stride, c_pitch);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================
+// log-mel pre/post passes (reference feature_extractor.py:207-214 zero-pad to 480000, torch.stft
+// center/reflect framing, :104-109 per-item max-8 clamp and (x+4)/4)
+// ================================================================================================
+constexpr int kMelSamples = 480000, kMelPad = 200, kMelFrames = 3000, kMelBins = 80;
+
+__global__ void mel_pad_kernel(const float* __restrict__ wav, long long wav_stride, int wav_cols,
+                               const long long* __restrict__ lens, float* __restrict__ padded,
+                               long long* __restrict__ mel_lens, float* __restrict__ item_max) {
+  const int b = blockIdx.y;
+  long long len = lens[b];
+  len = len < 0 ? 0 : (len > kMelSamples ? kMelSamples : len);
+  if (len > wav_cols) len = wav_cols;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (mel_lens) mel_lens[b] = (len + 159) / 160;
+    item_max[b] = -INFINITY;
+  }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kMelSamples + 2 * kMelPad) return;
+  int sidx = i - kMelPad;
+  if (sidx < 0) sidx = -sidx;
+  else if (sidx >= kMelSamples) sidx = 2 * (kMelSamples - 1) - sidx;
+  padded[(long long)b * (kMelSamples + 2 * kMelPad) + i] = (sidx < len) ? wav[(long long)b * wav_stride + sidx] : 0.f;
+}
+
+int mel_pad(const float* wav, long long wav_stride, int wav_cols, const long long* lens, int nb, float* padded,
+            long long* mel_lens, float* item_max, cudaStream_t s) {
+  dim3 grid(ceil_div(kMelSamples + 2 * kMelPad, 256), nb);
+  mel_pad_kernel<<<grid, 256, 0, s>>>(wav, wav_stride, wav_cols, lens, padded, mel_lens, item_max);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename TO>
+__global__ void mel_finalize_kernel(const float* __restrict__ logmel, const float* __restrict__ item_max,
+                                    float* __restrict__ mel_cf, TO* __restrict__ mel_cl, int cl_pitch) {
+  __shared__ float tile[32][kMelBins + 1];
+  const int b = blockIdx.y, t0 = blockIdx.x * 32;
+  const float floor_v = item_max[b] - 8.0f;
+  for (int i = threadIdx.x; i < 32 * kMelBins; i += blockDim.x) {
+    const int r = i / kMelBins, m = i % kMelBins;
+    const int t = t0 + r;
+    float v = 0.f;
+    if (t < kMelFrames) v = (fmaxf(logmel[((long long)b * kMelFrames + t) * kMelBins + m], floor_v) + 4.0f) / 4.0f;
+    tile[r][m] = v;
+  }
+  __syncthreads();
+  if (mel_cf) {
+    for (int i = threadIdx.x; i < 32 * kMelBins; i += blockDim.x) {
+      const int m = i / 32, r = i % 32;
+      if (t0 + r < kMelFrames) mel_cf[((long long)b * kMelBins + m) * kMelFrames + t0 + r] = tile[r][m];
+    }
+  }
+  if (mel_cl) {
+    for (int i = threadIdx.x; i < 32 * cl_pitch; i += blockDim.x) {
+      const int r = i / cl_pitch, m = i % cl_pitch;
+      if (t0 + r < kMelFrames)
+        mel_cl[((long long)b * kMelFrames + t0 + r) * cl_pitch + m] = from_f32<TO>(m < kMelBins ? tile[r][m] : 0.f);
+    }
+  }
+}
+
+int mel_finalize(const float* logmel, const float* item_max, int nb, float* mel_cf, void* mel_cl, int cl_type,
+                 int cl_pitch, cudaStream_t s) {
+  dim3 grid(ceil_div(kMelFrames, 32), nb);
+  if (cl_type == 0) mel_finalize_kernel<float><<<grid, 256, 0, s>>>(logmel, item_max, mel_cf, (float*)mel_cl, cl_pitch);
+  else mel_finalize_kernel<bf16><<<grid, 256, 0, s>>>(logmel, item_max, mel_cf, (bf16*)mel_cl, cl_pitch);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================
+// iSTFT overlap-add with "same" padding (reference modules.py:861-884): n_fft 640, hop 160.
+// out[s] = sum_t frames[t][p-160t] / sum_t w^2[p-160t],  p = s + 240, t in the <=4 overlapping frames.
+// ================================================================================================
+__global__ void istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ win_sq, int T,
+                                 float* __restrict__ wav) {
+  __shared__ float w2[640];
+  for (int i = threadIdx.x; i < 640; i += blockDim.x) w2[i] = win_sq[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int L = 160 * T;
+  if (sidx >= L) return;
+  const int p = sidx + 240;
+  const int t_hi = min(T - 1, p / 160);
+  const int t_lo = max(0, (p - 639 + 159) / 160);
+  float acc = 0.f, env = 0.f;
+  for (int t = t_lo; t <= t_hi; ++t) {
+    const int n = p - 160 * t;
+    acc += frames[((long long)b * T + t) * 640 + n];
+    env += w2[n];
+  }
+  wav[(long long)b * L + sidx] = acc / env;
+}
+
+int istft_ola(const float* frames, const float* win_sq, int nb, int T, float* wav, cudaStream_t s) {
+  dim3 grid(ceil_div(160 * T, 256), nb);
+  istft_ola_kernel<<<grid, 256, 0, s>>>(frames, win_sq, T, wav);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================
+__global__ void fill_f32_kernel(float* p, float v, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+int fill_f32(float* p, float v, long long n, cudaStream_t s) {
+  fill_f32_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, s>>>(p, v, n);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+__global__ void cvt_bf16_kernel(const float* in, bf16* out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+int convert_f32_to_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
+  cvt_bf16_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, s>>>(in, out, n);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace swc

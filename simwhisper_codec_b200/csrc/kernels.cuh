@@ -1,0 +1,50 @@
+// Launch wrappers of the bandwidth-bound / small kernels (kernels.cu, attention_simt.cu).
+// dtype codes: 0 = fp32, 1 = bf16.  All pointers are device pointers; nothing here synchronises.
+#pragma once
+#include "gemm.cuh"
+
+namespace swc {
+
+// LayerNorm over the last dim (C multiple of 256, <= 1024) of channel-last rows.
+// Output has t_out >= t_in rows per batch; rows t >= t_in or t >= lens[b] (if lens) are written as zero.
+int layernorm(const void* in, int in_type, void* out, int out_type, const float* gamma, const float* beta,
+              float eps, int nb, int t_in, int t_out, int C, const long long* lens, cudaStream_t s);
+
+// Vocos ConvNeXt front half: depthwise conv k7 (pad 3) + bias + LayerNorm(eps) over C=512. x fp32 (nb,T,C).
+int dwconv7_ln(const float* x, const float* w7c /*[7][C]*/, const float* bias, const float* gamma,
+               const float* beta, float eps, void* out, int out_type, int nb, int T, int C, cudaStream_t s);
+
+// Anti-aliased SnakeBeta along time of channel-last (nb,T,C): 2x up (12 taps) -> snake -> 2x down.
+int aa_snake(const void* in, int in_type, void* out, int out_type, const float* taps_up, const float* taps_dn,
+             const float* alpha_log, const float* beta_log, int nb, int T, int C, cudaStream_t s);
+
+// FSQ on channels-first fp32 latents (module-level quantizer.forward).
+int fsq_encode_cf(const float* latent_cf, const long long* lens, int nb, int T, const FsqConst& c,
+                  float* zq_cf, int* codes, float* zq_cl, cudaStream_t s);
+// codes (G=8, nb, T) int32/int64 -> zq (masked beyond lens)
+int fsq_decode(const void* codes, int codes_i64, const long long* lens, int nb, int T, const FsqConst& c,
+               float* zq_cf, float* zq_cl, cudaStream_t s);
+
+// layout conversion: channels-first fp32 (nb,C,T) <-> channel-last (nb,T_rows,Cpitch)
+int cf_to_cl(const float* in, void* out, int out_type, int nb, int C, int T, int t_rows, int c_pitch, cudaStream_t s);
+int cl_to_cf(const void* in, int in_type, float* out, int nb, int C, int T, long long in_batch_stride, int c_pitch, cudaStream_t s);
+
+// log-mel helpers
+int mel_pad(const float* wav, long long wav_stride, int wav_cols, const long long* lens, int nb,
+            float* padded /*(nb, 480400)*/, long long* mel_lens, float* item_max, cudaStream_t s);
+int mel_finalize(const float* logmel /*(nb,3000,80)*/, const float* item_max, int nb, float* mel_cf,
+                 void* mel_cl, int cl_type, int cl_pitch, cudaStream_t s);
+
+// iSTFT overlap-add ("same" padding): frames (nb,T,640) fp32 -> wav (nb,160T) fp32
+int istft_ola(const float* frames, const float* win_sq /*[640]*/, int nb, int T, float* wav, cudaStream_t s);
+
+// fp32 SIMT flash attention over fused qkv rows (nb*T, 3*H*64): q pre-scaled. Keys >= lens[b] masked.
+int attention_simt(const void* qkv, int type, void* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
+// bf16 tensor-core flash attention (mma.sync m16n8k16), same contract
+int attention_mma(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
+
+// misc
+int fill_f32(float* p, float v, long long n, cudaStream_t s);
+int convert_f32_to_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
+
+}  // namespace swc

@@ -1,0 +1,416 @@
+// Stage orchestration: which kernels run, on which channel-last buffers, for each reference module.
+// Everything is enqueued on the caller's stream; scratch comes from a bump arena over the caller's
+// workspace.  The same code runs in "dry" mode (no launches) to size the workspace.
+#include "pipeline.h"
+
+#include <algorithm>
+
+namespace swc {
+
+namespace {
+
+__global__ void lens_affine_kernel(const long long* in, long long* out, int n, long long mul, long long add, long long div) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    long long v = in[i];
+    if (v < 0) v = 0;
+    out[i] = (v * mul + add) / div;
+  }
+}
+
+int lens_affine(Ctx& c, const long long* in, long long* out, int n, long long mul, long long add, long long div) {
+  if (c.dry || !out) return 0;
+  lens_affine_kernel<<<ceil_div(n, 128), 128, 0, c.s>>>(in, out, n, mul, add, div);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t esz(int type) { return type == 0 ? 4 : 2; }
+
+GemmDesc base_desc(const void* A, long long a_row_stride, long long a_batch_stride, int a_rows, int a_cols,
+                   int m_rows, int nb, const LinearW& w) {
+  GemmDesc d{};
+  d.A = A; d.a_row_stride = a_row_stride; d.a_batch_stride = a_batch_stride; d.a_rows = a_rows; d.a_cols = a_cols;
+  d.m_rows = m_rows; d.nb = nb;
+  d.n_taps = 1; d.tap_row[0] = 0; d.tap_col[0] = 0; d.tap_k = w.K;
+  d.W = w.w; d.N = w.N; d.w_rows = w.w_rows;
+  d.epi.bias = w.bias;
+  d.epi.out_row_mul = 1; d.epi.out_row_off = 0;
+  d.epi.nb = nb;
+  return d;
+}
+
+void set_out(GemmDesc& d, void* out, long long row_stride, long long batch_stride) {
+  d.epi.out = out; d.epi.out_row_stride = row_stride; d.epi.out_batch_stride = batch_stride;
+}
+
+// dispatch on the model precision: bf16 operands go to the tcgen05 kernel, fp32 to the SIMT kernel
+int run_gemm(Ctx& c, const GemmDesc& d, int kind, int a_type, int out_type) {
+  if (c.dry) return 0;
+  if (a_type == 1 && !c.force_simt) return gemm_tc(d, kind, out_type, c.m->num_sms, c.s);
+  return gemm_simt(d, kind, a_type, out_type, c.s);
+}
+
+int run_attention(Ctx& c, const void* qkv, void* out, const long long* lens, int nb, int T) {
+  if (c.dry) return 0;
+  const int at = c.m->act_type();
+  if (at == 1 && !c.force_simt) return attention_mma((const bf16*)qkv, (bf16*)out, lens, nb, T, c.m->heads, c.s);
+  return attention_simt(qkv, at, out, lens, nb, T, c.m->heads, c.s);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// transformer stack shared by encoder and decoder (reference modules.py:214-232), h fp32 (nb,T,768)
+// ------------------------------------------------------------------------------------------------
+int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const long long* lens, int nb, int T) {
+  const Model& m = *c.m;
+  const int D = m.d_model, at = m.act_type();
+  const long long rows = (long long)nb * T;
+  const size_t mark = c.ws.mark();
+  void* xn = c.ws.alloc(rows * D * esz(at));
+  void* qkv = c.ws.alloc(rows * 3 * D * esz(at));
+  void* ao = c.ws.alloc(rows * D * esz(at));
+  void* ff = c.ws.alloc(rows * m.ffn * esz(at));
+  SWC_TRY(c.ws.check());
+  for (size_t li = 0; li < layers.size() && !c.dry; ++li) {
+    const LayerW& L = layers[li];
+    SWC_TRY(layernorm(h, 0, xn, at, L.ln1_g, L.ln1_b, 1e-5f, nb, T, T, D, nullptr, c.s));
+    {
+      GemmDesc d = base_desc(xn, D, 0, (int)std::min<long long>(rows, 0x7fffffff), D, (int)rows, 1, L.qkv);
+      set_out(d, qkv, 3 * D, 0);
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, at));
+    }
+    SWC_TRY(run_attention(c, qkv, ao, lens, nb, T));
+    {
+      GemmDesc d = base_desc(ao, D, 0, (int)rows, D, (int)rows, 1, L.out);
+      set_out(d, h, D, 0);
+      d.epi.residual = h; d.epi.res_row_stride = D; d.epi.res_batch_stride = 0;
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
+    }
+    SWC_TRY(layernorm(h, 0, xn, at, L.ln2_g, L.ln2_b, 1e-5f, nb, T, T, D, nullptr, c.s));
+    {
+      GemmDesc d = base_desc(xn, D, 0, (int)rows, D, (int)rows, 1, L.fc1);
+      set_out(d, ff, m.ffn, 0);
+      d.epi.act = 1;
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, at));
+    }
+    {
+      GemmDesc d = base_desc(ff, m.ffn, 0, (int)rows, m.ffn, (int)rows, 1, L.fc2);
+      set_out(d, h, D, 0);
+      d.epi.residual = h; d.epi.res_row_stride = D; d.epi.res_batch_stride = 0;
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
+    }
+  }
+  c.ws.release(mark);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder (reference modules.py:287-376).  mel_cl (nb,Tm,128) act type -> enc_cl (nb,T4,768) act type
+// with T = ceil(Tm/2) tokens, T4 = T rounded up to a multiple of 4 (zero rows), rows >= lens zeroed.
+// ------------------------------------------------------------------------------------------------
+int encoder_cl(Ctx& c, const void* mel_cl, const long long* enc_lens, int nb, int Tm, void* enc_cl) {
+  const Model& m = *c.m;
+  const int D = m.d_model, MP = m.mel_pitch, at = m.act_type();
+  const int T = (Tm + 1) / 2, T4 = (T + 3) / 4 * 4;
+  const size_t mark = c.ws.mark();
+  void* stem = c.ws.alloc((long long)nb * 2 * T * D * esz(at));
+  float* h = (float*)c.ws.alloc((long long)nb * T * D * 4);
+  SWC_TRY(c.ws.check());
+  if (!c.dry) {
+    if (Tm & 1) SWC_CHECK_CUDA(cudaMemsetAsync(stem, 0, (size_t)nb * 2 * T * D * esz(at), c.s));
+    {   // conv1: k3, pad 1, no activation
+      GemmDesc d = base_desc(mel_cl, MP, (long long)Tm * MP, Tm, MP, Tm, nb, m.conv1);
+      d.n_taps = 3; d.tap_k = MP;
+      for (int k = 0; k < 3; ++k) { d.tap_row[k] = k - 1; d.tap_col[k] = 0; }
+      set_out(d, stem, D, (long long)2 * T * D);
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, at));
+    }
+    {   // conv2: k3, stride 2, pad 1 on the (row-pair) view of the stem: token j reads frames 2j-1, 2j, 2j+1
+      GemmDesc d = base_desc(stem, 2 * D, (long long)2 * T * D, T, 2 * D, T, nb, m.conv2);
+      d.n_taps = 3; d.tap_k = D;
+      d.tap_row[0] = -1; d.tap_col[0] = D;
+      d.tap_row[1] = 0; d.tap_col[1] = 0;
+      d.tap_row[2] = 0; d.tap_col[2] = D;
+      set_out(d, h, D, (long long)T * D);
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
+    }
+  }
+  SWC_TRY(transformer_stack(c, m.enc_layers, h, enc_lens, nb, T));
+  if (!c.dry) SWC_TRY(layernorm(h, 0, enc_cl, at, m.enc_ln_g, m.enc_ln_b, 1e-5f, nb, T, T4, D, enc_lens, c.s));
+  c.ws.release(mark);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual units shared by the down- and up-sampler (reference modules.py:37-49); x fp32 (nb,Tc,512)
+// ------------------------------------------------------------------------------------------------
+static int residual_units(Ctx& c, const ResUnitW* R, float* x, bf16* x_bf_last, int nb, int Tc) {
+  const Model& m = *c.m;
+  const int H = m.hidden, at = m.act_type();
+  const long long rows = (long long)nb * Tc;
+  const size_t mark = c.ws.mark();
+  void* a = c.ws.alloc(rows * H * esz(at));
+  void* cbuf = c.ws.alloc(rows * H * esz(at));
+  SWC_TRY(c.ws.check());
+  for (int i = 0; i < 3 && !c.dry; ++i) {
+    const ResUnitW& r = R[i];
+    SWC_TRY(aa_snake(x, 0, a, at, r.fu0, r.fd0, r.a0, r.b0, nb, Tc, H, c.s));
+    {
+      GemmDesc d = base_desc(a, H, (long long)Tc * H, Tc, H, Tc, nb, r.conv7);
+      d.n_taps = 7; d.tap_k = H;
+      for (int k = 0; k < 7; ++k) { d.tap_row[k] = (k - 3) * r.dilation; d.tap_col[k] = 0; }
+      set_out(d, cbuf, H, (long long)Tc * H);
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, at));
+    }
+    SWC_TRY(aa_snake(cbuf, at, a, at, r.fu2, r.fd2, r.a2, r.b2, nb, Tc, H, c.s));
+    {
+      GemmDesc d = base_desc(a, H, 0, (int)rows, H, (int)rows, 1, r.conv1);
+      set_out(d, x, H, 0);
+      d.epi.residual = x; d.epi.res_row_stride = H;
+      if (i == 2) d.epi.out2 = x_bf_last;
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
+    }
+  }
+  c.ws.release(mark);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// down-sampler + FSQ (reference modules.py:519-550, quantizer.py:273-290)
+// enc_cl (nb,T4,768): T4 multiple of 4, rows beyond the real T are zero (the reference zero-pads).
+// ------------------------------------------------------------------------------------------------
+int downsample_fsq(Ctx& c, const void* enc_cl, const long long* code_lens, int nb, int T4, int* codes, float* zq_cf,
+                   float* latent_cf, float* zq_cl) {
+  const Model& m = *c.m;
+  const int D = m.d_model, H = m.hidden, at = m.act_type();
+  const int Tc = T4 / 4;
+  const size_t mark = c.ws.mark();
+  float* x = (float*)c.ws.alloc((long long)nb * Tc * H * 4);
+  bf16* xb = at == 1 ? (bf16*)c.ws.alloc((long long)nb * Tc * H * 2) : nullptr;
+  SWC_TRY(c.ws.check());
+  if (!c.dry) {
+    GemmDesc d = base_desc(enc_cl, 4 * D, (long long)T4 * D, Tc, 4 * D, Tc, nb, m.dn_in);
+    set_out(d, x, H, (long long)Tc * H);
+    SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
+  }
+  SWC_TRY(residual_units(c, m.dn_res, x, xb, nb, Tc));
+  if (!c.dry) {
+    GemmDesc d = base_desc(at == 1 ? (const void*)xb : (const void*)x, H, (long long)Tc * H, Tc, H, Tc, nb, m.dn_latent);
+    d.epi.lens = code_lens; d.epi.codes = codes; d.epi.zq_cf = zq_cf; d.epi.latent_cf = latent_cf; d.epi.zq_cl = zq_cl;
+    d.epi.fsq = m.fsq;
+    SWC_TRY(run_gemm(c, d, EPI_FSQ, at, 0));
+  }
+  c.ws.release(mark);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// up-sampler (reference modules.py:601-631): zq_cl fp32 (nb,Tc,32) -> h fp32 (nb,4Tc,768)
+// ------------------------------------------------------------------------------------------------
+int upsample_cl(Ctx& c, const float* zq_cl, int nb, int Tc, float* h) {
+  const Model& m = *c.m;
+  const int D = m.d_model, H = m.hidden, at = m.act_type();
+  const size_t mark = c.ws.mark();
+  float* x = (float*)c.ws.alloc((long long)nb * Tc * H * 4);
+  bf16* xb = at == 1 ? (bf16*)c.ws.alloc((long long)nb * Tc * H * 2) : nullptr;
+  SWC_TRY(c.ws.check());
+  if (!c.dry) {   // from_latent: K = 32, always the fp32 SIMT kernel
+    GemmDesc d = base_desc(zq_cl, m.latent, 0, nb * Tc, m.latent, nb * Tc, 1, m.up_from);
+    set_out(d, x, H, 0);
+    SWC_TRY(gemm_simt(d, EPI_STORE, 0, 0, c.s));
+  }
+  SWC_TRY(residual_units(c, m.up_res, x, xb, nb, Tc));
+  if (!c.dry) {   // to_stacked with rows ordered (s, d): output row t' of width 3072 == 4 token rows of 768
+    GemmDesc d = base_desc(at == 1 ? (const void*)xb : (const void*)x, H, 0, nb * Tc, H, nb * Tc, 1, m.up_stacked);
+    set_out(d, h, 4 * D, 0);
+    SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
+  }
+  c.ws.release(mark);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder (reference modules.py:437-474): h fp32 (nb,T,768) (destroyed) -> mel_cl (nb,2T,128) act type
+// ------------------------------------------------------------------------------------------------
+int decoder_cl(Ctx& c, float* h, const long long* lens, int nb, int T, void* mel_cl) {
+  const Model& m = *c.m;
+  const int D = m.d_model, MP = m.mel_pitch, at = m.act_type();
+  SWC_TRY(transformer_stack(c, m.dec_layers, h, lens, nb, T));
+  const size_t mark = c.ws.mark();
+  void* y = c.ws.alloc((long long)nb * T * D * esz(at));
+  void* z = c.ws.alloc((long long)nb * 2 * T * D * esz(at));
+  SWC_TRY(c.ws.check());
+  if (!c.dry) {
+    SWC_TRY(layernorm(h, 0, y, at, m.dec_ln_g, m.dec_ln_b, 1e-5f, nb, T, T, D, lens, c.s));
+    {   // deconv1 even output rows 2t: taps h[t-1] (k=2), h[t] (k=0)
+      GemmDesc d = base_desc(y, D, (long long)T * D, T, D, T, nb, m.deconv1_even);
+      d.n_taps = 2; d.tap_k = D;
+      d.tap_row[0] = -1; d.tap_row[1] = 0; d.tap_col[0] = d.tap_col[1] = 0;
+      set_out(d, z, D, (long long)2 * T * D);
+      d.epi.out_row_mul = 2; d.epi.out_row_off = 0;
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, at));
+    }
+    {   // odd output rows 2t+1: tap h[t] (k=1)
+      GemmDesc d = base_desc(y, D, (long long)T * D, T, D, T, nb, m.deconv1_odd);
+      set_out(d, z, D, (long long)2 * T * D);
+      d.epi.out_row_mul = 2; d.epi.out_row_off = 1;
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, at));
+    }
+    {   // deconv2 (k3, stride 1), first 2T outputs: o[u] = sum_k W2_k^T z[u-k]
+      GemmDesc d = base_desc(z, D, (long long)2 * T * D, 2 * T, D, 2 * T, nb, m.deconv2);
+      d.n_taps = 3; d.tap_k = D;
+      for (int k = 0; k < 3; ++k) { d.tap_row[k] = -k; d.tap_col[k] = 0; }
+      set_out(d, mel_cl, MP, (long long)2 * T * MP);
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, at));
+    }
+  }
+  c.ws.release(mark);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Vocos backbone + ISTFT head (reference modules.py:1492-1504, 1229-1248, 1064-1082, 831-886)
+// mel_cl (nb,Tv,128) act type -> wav fp32 (nb,160 Tv).  No length masking anywhere.
+// ------------------------------------------------------------------------------------------------
+int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav) {
+  const Model& m = *c.m;
+  const int V = m.voc_dim, I = m.voc_inter, MP = m.mel_pitch, at = m.act_type();
+  const long long rows = (long long)nb * Tv;
+  const int NP = m.voc_head.N;
+  const size_t mark = c.ws.mark();
+  float* x = (float*)c.ws.alloc(rows * V * 4);
+  void* y = c.ws.alloc(rows * V * esz(at));
+  // the 4096-wide hidden, the spectrum and the frames are never live together: share one region
+  const size_t big = std::max<size_t>((size_t)rows * I * esz(at), (size_t)rows * (NP + m.n_fft) * 4);
+  char* region = (char*)c.ws.alloc(big);
+  SWC_TRY(c.ws.check());
+  if (!c.dry) {
+    void* g = region;
+    float* e = (float*)region;     // embed output (fp32) lives in the region until the first LayerNorm
+    {
+      GemmDesc d = base_desc(mel_cl, MP, (long long)Tv * MP, Tv, MP, Tv, nb, m.voc_embed);
+      d.n_taps = 7; d.tap_k = MP;
+      for (int k = 0; k < 7; ++k) { d.tap_row[k] = k - 3; d.tap_col[k] = 0; }
+      set_out(d, e, V, (long long)Tv * V);
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
+    }
+    SWC_TRY(layernorm(e, 0, x, 0, m.voc_norm_g, m.voc_norm_b, 1e-6f, nb, Tv, Tv, V, nullptr, c.s));
+    for (const VocosBlockW& B : m.voc_blocks) {
+      SWC_TRY(dwconv7_ln(x, B.dw_w, B.dw_b, B.ln_g, B.ln_b, 1e-6f, y, at, nb, Tv, V, c.s));
+      {
+        GemmDesc d = base_desc(y, V, 0, (int)rows, V, (int)rows, 1, B.pw1);
+        set_out(d, g, I, 0);
+        d.epi.act = 1;
+        SWC_TRY(run_gemm(c, d, EPI_STORE, at, at));
+      }
+      {
+        GemmDesc d = base_desc(g, I, 0, (int)rows, I, (int)rows, 1, B.pw2);
+        set_out(d, x, V, 0);
+        d.epi.gamma = B.gamma;
+        d.epi.residual = x; d.epi.res_row_stride = V;
+        SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
+      }
+    }
+    SWC_TRY(layernorm(x, 0, y, at, m.voc_final_g, m.voc_final_b, 1e-6f, nb, Tv, Tv, V, nullptr, c.s));
+    float* S = (float*)region;
+    float* frames = S + rows * NP;
+    {   // head GEMM with exp/clip/sincos epilogue -> interleaved complex spectrum (fp32)
+      GemmDesc d = base_desc(y, V, 0, (int)rows, V, (int)rows, 1, m.voc_head);
+      set_out(d, S, NP, 0);
+      SWC_TRY(run_gemm(c, d, EPI_HEAD, at, 0));
+    }
+    {   // windowed inverse real DFT as an fp32 GEMM
+      LinearW wi; wi.w = m.w_idft; wi.bias = nullptr; wi.N = m.n_fft; wi.w_rows = m.n_fft; wi.K = NP;
+      GemmDesc d = base_desc(S, NP, 0, (int)rows, NP, (int)rows, 1, wi);
+      set_out(d, frames, m.n_fft, 0);
+      SWC_TRY(gemm_simt(d, EPI_STORE, 0, 0, c.s));
+    }
+    SWC_TRY(istft_ola(frames, m.win_sq, nb, Tv, wav, c.s));
+  }
+  c.ws.release(mark);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// log-mel (reference feature_extractor.py:86-112, 136-245): wav -> mel_cf fp32 / mel_cl act type
+// ------------------------------------------------------------------------------------------------
+int mel_frontend(Ctx& c, const float* wav, long long wav_stride, int wav_cols, const long long* lens, int nb,
+                 float* mel_cf, void* mel_cl, long long* mel_lens) {
+  const Model& m = *c.m;
+  const size_t mark = c.ws.mark();
+  float* padded = (float*)c.ws.alloc((long long)nb * 480400 * 4);
+  float* power = (float*)c.ws.alloc((long long)nb * 3000 * 208 * 4);
+  float* logmel = (float*)c.ws.alloc((long long)nb * 3000 * 80 * 4);
+  float* item_max = (float*)c.ws.alloc((long long)nb * 4);
+  SWC_TRY(c.ws.check());
+  if (!c.dry) {
+    SWC_TRY(mel_pad(wav, wav_stride, wav_cols, lens, nb, padded, mel_lens, item_max, c.s));
+    {   // frames are rows of the padded signal at stride 160; Hann window folded into the DFT operand
+      LinearW w; w.w = m.w_dft; w.bias = nullptr; w.N = 416; w.w_rows = 416; w.K = 400;
+      GemmDesc d = base_desc(padded, 160, 480400, 3000, 400, 3000, nb, w);
+      set_out(d, power, 208, (long long)3000 * 208);
+      SWC_TRY(gemm_simt(d, EPI_POWER, 0, 0, c.s));
+    }
+    {
+      LinearW w; w.w = m.w_melfb; w.bias = nullptr; w.N = 80; w.w_rows = 80; w.K = 208;
+      GemmDesc d = base_desc(power, 208, (long long)3000 * 208, 3000, 208, 3000, nb, w);
+      set_out(d, logmel, 80, (long long)3000 * 80);
+      d.epi.item_max = item_max;
+      SWC_TRY(gemm_simt(d, EPI_LOGMEL, 0, 0, c.s));
+    }
+    SWC_TRY(mel_finalize(logmel, item_max, nb, mel_cf, mel_cl, m.act_type(), m.mel_pitch, c.s));
+  }
+  c.ws.release(mark);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused chains
+// ------------------------------------------------------------------------------------------------
+int tokenize_chain(Ctx& c, const float* wav, long long wav_stride, int wav_cols, const long long* lens, int nb,
+                   int* codes, float* zq_cf, long long* codes_lens) {
+  const Model& m = *c.m;
+  const int at = m.act_type(), Tm = 3000, T = 1500, T4 = 1500;
+  const size_t mark = c.ws.mark();
+  void* mel_cl = c.ws.alloc((long long)nb * Tm * m.mel_pitch * esz(at));
+  void* enc_cl = c.ws.alloc((long long)nb * T4 * m.d_model * esz(at));
+  long long* mel_lens = (long long*)c.ws.alloc(nb * 8);
+  long long* enc_lens = (long long*)c.ws.alloc(nb * 8);
+  long long* code_lens = (long long*)c.ws.alloc(nb * 8);
+  SWC_TRY(c.ws.check());
+  SWC_TRY(mel_frontend(c, wav, wav_stride, wav_cols, lens, nb, nullptr, mel_cl, mel_lens));
+  SWC_TRY(lens_affine(c, mel_lens, enc_lens, nb, 1, 0, 2));
+  SWC_TRY(lens_affine(c, enc_lens, code_lens, nb, 1, 3, 4));
+  SWC_TRY(lens_affine(c, code_lens, codes_lens, nb, 1, 0, 1));
+  SWC_TRY(encoder_cl(c, mel_cl, enc_lens, nb, Tm, enc_cl));
+  SWC_TRY(downsample_fsq(c, enc_cl, code_lens, nb, T4, codes, zq_cf, nullptr, nullptr));
+  (void)T;
+  c.ws.release(mark);
+  return 0;
+}
+
+int detokenize_chain(Ctx& c, const float* zq_cl, const long long* code_lens, int nb, int Tc, float* wav,
+                     long long* out_lens) {
+  const Model& m = *c.m;
+  const int at = m.act_type(), T = 4 * Tc, Tv = 8 * Tc;
+  const size_t mark = c.ws.mark();
+  float* h = (float*)c.ws.alloc((long long)nb * T * m.d_model * 4);
+  void* mel_cl = c.ws.alloc((long long)nb * Tv * m.mel_pitch * esz(at));
+  long long* tok_lens = (long long*)c.ws.alloc(nb * 8);
+  SWC_TRY(c.ws.check());
+  SWC_TRY(lens_affine(c, code_lens, tok_lens, nb, 4, 0, 1));
+  SWC_TRY(lens_affine(c, code_lens, out_lens, nb, 1280, 0, 1));
+  SWC_TRY(upsample_cl(c, zq_cl, nb, Tc, h));
+  SWC_TRY(decoder_cl(c, h, tok_lens, nb, T, mel_cl));
+  SWC_TRY(vocos_cl(c, mel_cl, nb, Tv, wav));
+  c.ws.release(mark);
+  return 0;
+}
+
+int lens_affine_pub(Ctx& c, const long long* in, long long* out, int n, long long mul, long long add, long long div) {
+  return lens_affine(c, in, out, n, mul, add, div);
+}
+
+}  // namespace swc
