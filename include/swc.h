@@ -119,6 +119,14 @@ int swc_forward(const swc_model* m, const float* mel_cf, const int64_t* mel_lens
                 float* wav, int64_t* out_lens, int32_t* codes /* optional (8,B,Tc) */, void* workspace,
                 size_t ws_bytes, void* stream);
 
+/* ---- launch accounting: every kernel launch is counted per class (0 tcgen05 GEMM, 1 SIMT GEMM,
+ *      2 attention, 3 LayerNorm, 4 dwconv+LayerNorm, 5 anti-aliased snake, 6 other); with
+ *      enable_timing != 0 each launch is also bracketed by CUDA events on its stream.
+ *      swc_profile() resets; swc_profile_read() synchronises on the recorded events and returns
+ *      per-class milliseconds and launch counts (arrays of >= 7 entries). ---- */
+void swc_profile(int enable_timing);
+int swc_profile_read(double* ms_per_class, int64_t* launches_per_class, int n);
+
 /* ---- low-level operator hooks used by the unit tests (GEMM back ends, attention) ---- */
 int swc_test_gemm(int backend /*0 simt fp32, 1 simt bf16, 2 tcgen05 bf16*/, const void* A, const void* W,
                   const float* bias, void* out, int out_bf16, int M, int N, int K, int act, void* stream);

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libswc.so")
 
 PRECISION = {"fp32": 0, "bf16": 1}
+KCLASS = ("gemm_tcgen05", "gemm_simt_fp32", "attention", "layernorm", "dwconv7_ln", "aa_snake", "other")
 STAGE = {"mel": 0, "encoder": 1, "downsample": 2, "quantizer": 3, "upsample": 4, "decoder": 5, "vocos": 6,
          "tokenize": 7, "detokenize": 8, "forward": 9}
 
@@ -40,6 +41,8 @@ SIGNATURES = {
     "swc_tokenize": (_i, [_p, _p, _i64, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "swc_detokenize": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p, _sz, _p]),
     "swc_forward": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "swc_profile": (None, [_i]),
+    "swc_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(_i64), _i]),
     "swc_test_gemm": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "swc_test_attention": (_i, [_i, _p, _p, _p, _i, _i, _i, _p]),
 }

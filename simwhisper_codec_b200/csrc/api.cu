@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "../../include/swc.h"
 #include "pipeline.h"
@@ -15,6 +16,35 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+struct ProfState {
+  bool timing = false;
+  long long launches[KC_COUNT] = {0};
+  struct Rec { int cls; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t cur = nullptr;
+};
+static ProfState g_prof;
+static cudaEvent_t prof_event() {
+  if (!g_prof.pool.empty()) { cudaEvent_t e = g_prof.pool.back(); g_prof.pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(int cls, cudaStream_t s) {
+  g_prof.launches[cls]++;
+  if (!g_prof.timing) return;
+  g_prof.cur = prof_event();
+  cudaEventRecord(g_prof.cur, s);
+}
+void prof_end(int cls, cudaStream_t s) {
+  if (!g_prof.timing || !g_prof.cur) return;
+  cudaEvent_t b = prof_event();
+  cudaEventRecord(b, s);
+  g_prof.recs.push_back({cls, g_prof.cur, b});
+  g_prof.cur = nullptr;
 }
 }  // namespace swc
 
@@ -295,6 +325,29 @@ int swc_forward(const swc_model* m, const float* mel_cf, const int64_t* mel_lens
                 int64_t* out_lens, int32_t* codes, void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();
   return stage_forward(c, mel_cf, (const long long*)mel_lens, batch, mel_frames, wav, (long long*)out_lens, codes);
+}
+
+void swc_profile(int enable_timing) {
+  g_prof.timing = enable_timing != 0;
+  for (int i = 0; i < KC_COUNT; ++i) g_prof.launches[i] = 0;
+  for (auto& r : g_prof.recs) { g_prof.pool.push_back(r.a); g_prof.pool.push_back(r.b); }
+  g_prof.recs.clear();
+}
+
+int swc_profile_read(double* ms_per_class, int64_t* launches_per_class, int n) {
+  SWC_REQUIRE(n >= KC_COUNT, "swc_profile_read: need room for %d classes", (int)KC_COUNT);
+  for (int i = 0; i < n; ++i) { ms_per_class[i] = 0.0; launches_per_class[i] = 0; }
+  for (auto& r : g_prof.recs) {
+    SWC_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    SWC_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_per_class[r.cls] += ms;
+    g_prof.pool.push_back(r.a);
+    g_prof.pool.push_back(r.b);
+  }
+  g_prof.recs.clear();
+  for (int i = 0; i < KC_COUNT; ++i) launches_per_class[i] = g_prof.launches[i];
+  return 0;
 }
 
 int swc_test_gemm(int backend, const void* A, const void* W, const float* bias, void* out, int out_bf16, int M, int N, int K,

@@ -168,6 +168,7 @@ int attention_simt(const void* qkv, int type, void* out, const long long* lens, 
     SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
+  ProfScope ps(KC_ATTN, s);
   if (type == 0) attention_simt_kernel<float><<<grid, 256, kSmemBytes, s>>>((const float*)qkv, (float*)out, lens, T, H);
   else attention_simt_kernel<bf16><<<grid, 256, kSmemBytes, s>>>((const bf16*)qkv, (bf16*)out, lens, T, H);
   SWC_CHECK_CUDA(cudaGetLastError());

@@ -31,6 +31,16 @@ void set_error(const char* fmt, ...);
     if (_r != 0) return _r;                                                                    \
   } while (0)
 
+// ---- per-kernel-class launch counters and (optional) CUDA-event timers ------------------------------
+enum KClass { KC_GEMM_TC = 0, KC_GEMM_SIMT, KC_ATTN, KC_LAYERNORM, KC_DWCONV_LN, KC_SNAKE, KC_MISC, KC_COUNT };
+void prof_begin(int cls, cudaStream_t s);
+void prof_end(int cls, cudaStream_t s);
+struct ProfScope {
+  int cls; cudaStream_t s;
+  ProfScope(int c, cudaStream_t st) : cls(c), s(st) { prof_begin(cls, s); }
+  ~ProfScope() { prof_end(cls, s); }
+};
+
 // ---- element conversion ------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

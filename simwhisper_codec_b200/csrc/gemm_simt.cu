@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(GemmDesc d) {
 template <typename TA, int KIND, typename TO>
 int launch(const GemmDesc& d, cudaStream_t s) {
   dim3 grid(ceil_div(d.N, BN), ceil_div(d.m_rows, BM), d.nb);
+  ProfScope ps(KC_GEMM_SIMT, s);
   gemm_simt_kernel<TA, KIND, TO><<<grid, 256, 0, s>>>(d);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -328,6 +328,7 @@ int launch(const GemmDesc& d, int num_sms, cudaStream_t s) {
   }
   const long long total = (long long)p.m_tiles * p.n_tiles * p.nb;
   const int grid = (int)std::min<long long>(total, num_sms);
+  ProfScope ps(KC_GEMM_TC, s);
   kern<<<grid, kThreads, L::kTotal, s>>>(tmA, tmW, p);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -61,6 +61,7 @@ static int layernorm_t(const void* in, void* out, const float* g, const float* b
   const long long rows = (long long)nb * t_out;
   const int warps = 8;
   dim3 grid((unsigned)ceil_div_ll(rows, warps));
+  ProfScope ps(KC_LAYERNORM, s);
   if (C == 768) layernorm_kernel<TI, TO, 3><<<grid, warps * 32, 0, s>>>((const TI*)in, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
   else if (C == 512) layernorm_kernel<TI, TO, 2><<<grid, warps * 32, 0, s>>>((const TI*)in, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
   else if (C == 256) layernorm_kernel<TI, TO, 1><<<grid, warps * 32, 0, s>>>((const TI*)in, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
@@ -140,6 +141,7 @@ int dwconv7_ln(const float* x, const float* w7c, const float* bias, const float*
   SWC_REQUIRE(C == 512, "dwconv7_ln: only C=512 is built (got %d)", C);
   const long long rows = (long long)nb * T;
   dim3 grid((unsigned)ceil_div_ll(rows, 8));
+  ProfScope ps(KC_DWCONV_LN, s);
   if (out_type == 0) dwconv7_ln_kernel<float, 2><<<grid, 256, 0, s>>>(x, w7c, bias, gamma, beta, eps, (float*)out, nb, T);
   else dwconv7_ln_kernel<bf16, 2><<<grid, 256, 0, s>>>(x, w7c, bias, gamma, beta, eps, (bf16*)out, nb, T);
   SWC_CHECK_CUDA(cudaGetLastError());
@@ -212,6 +214,7 @@ __global__ void __launch_bounds__(128) aa_snake_kernel(const TI* __restrict__ in
 int aa_snake(const void* in, int in_type, void* out, int out_type, const float* taps_up, const float* taps_dn,
              const float* alpha_log, const float* beta_log, int nb, int T, int C, cudaStream_t s) {
   dim3 grid(ceil_div(C, 128), ceil_div(T, kSnakeChunk), nb);
+  ProfScope ps(KC_SNAKE, s);
   if (in_type == 0 && out_type == 0) aa_snake_kernel<float, float><<<grid, 128, 0, s>>>((const float*)in, (float*)out, taps_up, taps_dn, alpha_log, beta_log, T, C);
   else if (in_type == 0 && out_type == 1) aa_snake_kernel<float, bf16><<<grid, 128, 0, s>>>((const float*)in, (bf16*)out, taps_up, taps_dn, alpha_log, beta_log, T, C);
   else if (in_type == 1 && out_type == 1) aa_snake_kernel<bf16, bf16><<<grid, 128, 0, s>>>((const bf16*)in, (bf16*)out, taps_up, taps_dn, alpha_log, beta_log, T, C);
@@ -247,6 +250,7 @@ __global__ void fsq_encode_cf_kernel(const float* __restrict__ z, const long lon
 int fsq_encode_cf(const float* latent_cf, const long long* lens, int nb, int T, const FsqConst& c, float* zq_cf,
                   int* codes, float* zq_cl, cudaStream_t s) {
   const long long total = 8LL * nb * T;
+  ProfScope ps(KC_MISC, s);
   fsq_encode_cf_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, s>>>(latent_cf, lens, nb, T, c, zq_cf, codes, zq_cl);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -278,6 +282,7 @@ int fsq_decode(const void* codes, int codes_i64, const long long* lens, int nb, 
                float* zq_cf, float* zq_cl, cudaStream_t s) {
   const long long total = 8LL * nb * T;
   const unsigned grid = (unsigned)ceil_div_ll(total, 256);
+  ProfScope ps(KC_MISC, s);
   if (codes_i64) fsq_decode_kernel<long long><<<grid, 256, 0, s>>>((const long long*)codes, lens, nb, T, c, zq_cf, zq_cl);
   else fsq_decode_kernel<int><<<grid, 256, 0, s>>>((const int*)codes, lens, nb, T, c, zq_cf, zq_cl);
   SWC_CHECK_CUDA(cudaGetLastError());
@@ -306,6 +311,7 @@ __global__ void cf_to_cl_kernel(const float* __restrict__ in, TO* __restrict__ o
 
 int cf_to_cl(const float* in, void* out, int out_type, int nb, int C, int T, int t_rows, int c_pitch, cudaStream_t s) {
   dim3 grid(ceil_div(t_rows, 32), ceil_div(c_pitch, 32), nb), block(32, 8);
+  ProfScope ps(KC_MISC, s);
   if (out_type == 0) cf_to_cl_kernel<float><<<grid, block, 0, s>>>(in, (float*)out, C, T, t_rows, c_pitch);
   else cf_to_cl_kernel<bf16><<<grid, block, 0, s>>>(in, (bf16*)out, C, T, t_rows, c_pitch);
   SWC_CHECK_CUDA(cudaGetLastError());
@@ -332,6 +338,7 @@ __global__ void cl_to_cf_kernel(const TI* __restrict__ in, float* __restrict__ o
 
 int cl_to_cf(const void* in, int in_type, float* out, int nb, int C, int T, long long in_batch_stride, int c_pitch, cudaStream_t s) {
   dim3 grid(ceil_div(T, 32), ceil_div(C, 32), nb), block(32, 8);
+  ProfScope ps(KC_MISC, s);
   if (in_type == 0) cl_to_cf_kernel<float><<<grid, block, 0, s>>>((const float*)in, out, C, T, in_batch_stride, c_pitch);
   else cl_to_cf_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)in, out, C, T, in_batch_stride, c_pitch);
   SWC_CHECK_CUDA(cudaGetLastError());
@@ -366,6 +373,7 @@ __global__ void mel_pad_kernel(const float* __restrict__ wav, long long wav_stri
 int mel_pad(const float* wav, long long wav_stride, int wav_cols, const long long* lens, int nb, float* padded,
             long long* mel_lens, float* item_max, cudaStream_t s) {
   dim3 grid(ceil_div(kMelSamples + 2 * kMelPad, 256), nb);
+  ProfScope ps(KC_MISC, s);
   mel_pad_kernel<<<grid, 256, 0, s>>>(wav, wav_stride, wav_cols, lens, padded, mel_lens, item_max);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -403,6 +411,7 @@ __global__ void mel_finalize_kernel(const float* __restrict__ logmel, const floa
 int mel_finalize(const float* logmel, const float* item_max, int nb, float* mel_cf, void* mel_cl, int cl_type,
                  int cl_pitch, cudaStream_t s) {
   dim3 grid(ceil_div(kMelFrames, 32), nb);
+  ProfScope ps(KC_MISC, s);
   if (cl_type == 0) mel_finalize_kernel<float><<<grid, 256, 0, s>>>(logmel, item_max, mel_cf, (float*)mel_cl, cl_pitch);
   else mel_finalize_kernel<bf16><<<grid, 256, 0, s>>>(logmel, item_max, mel_cf, (bf16*)mel_cl, cl_pitch);
   SWC_CHECK_CUDA(cudaGetLastError());
@@ -436,6 +445,7 @@ __global__ void istft_ola_kernel(const float* __restrict__ frames, const float* 
 
 int istft_ola(const float* frames, const float* win_sq, int nb, int T, float* wav, cudaStream_t s) {
   dim3 grid(ceil_div(160 * T, 256), nb);
+  ProfScope ps(KC_MISC, s);
   istft_ola_kernel<<<grid, 256, 0, s>>>(frames, win_sq, T, wav);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -447,6 +457,7 @@ __global__ void fill_f32_kernel(float* p, float v, long long n) {
   if (i < n) p[i] = v;
 }
 int fill_f32(float* p, float v, long long n, cudaStream_t s) {
+  ProfScope ps(KC_MISC, s);
   fill_f32_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, s>>>(p, v, n);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -456,6 +467,7 @@ __global__ void cvt_bf16_kernel(const float* in, bf16* out, long long n) {
   if (i < n) out[i] = __float2bfloat16_rn(in[i]);
 }
 int convert_f32_to_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
+  ProfScope ps(KC_MISC, s);
   cvt_bf16_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, s>>>(in, out, n);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -20,6 +20,7 @@ __global__ void lens_affine_kernel(const long long* in, long long* out, int n, l
 
 int lens_affine(Ctx& c, const long long* in, long long* out, int n, long long mul, long long add, long long div) {
   if (c.dry || !out) return 0;
+  ProfScope ps(KC_MISC, c.s);
   lens_affine_kernel<<<ceil_div(n, 128), 128, 0, c.s>>>(in, out, n, mul, add, div);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
