@@ -30,7 +30,7 @@ struct EpiParams {
   const float* gamma;       // [N] or null
   const float* residual;    // fp32, may alias out
   long long res_row_stride, res_batch_stride;
-  int act;                  // 0 none, 1 exact GELU
+  int act;                  // 0 none, 1 exact-erf GELU (erff), 2 erf GELU via gelu_fast (bf16 outputs)
   void* out;                // TO
   long long out_row_stride, out_batch_stride;
   int out_row_mul, out_row_off;   // output row = m * mul + off (deconv parity interleave)
@@ -83,22 +83,45 @@ __device__ __forceinline__ int fsq_quantize4(const FsqConst& c, const float* x, 
 // ------------------------------------------------------------------------------------------------
 // epilogue on 8 consecutive columns [n0, n0+8) of row m of batch b
 // ------------------------------------------------------------------------------------------------
+// exact-erf GELU to ~2.5e-5 absolute: erf(x/sqrt2) ~ tanh(x (c0 + c1 x^2 + c2 x^4)), one MUFU.TANH.
+// Used only where the result is rounded to bf16 (half-ulp there is >= 1e-3 relative).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float x2 = fminf(x * x, 36.0f);
+  const float poly = fmaf(fmaf(-0.000351517274f, x2, 0.0370056493f), x2, 0.79750788f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * poly));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
 template <int KIND, typename TO>
 __device__ __forceinline__ void epi_apply(const EpiParams& p, int b, int m, int n0, int N, int m_rows,
-                                          float (&v)[8]) {
+                                          float (&v)[8], const float* bias8, const float* gamma8) {
+  // bias8 / gamma8 point at the 8 per-column values of this chunk (global or shared memory) or are null
   if constexpr (KIND == EPI_STORE) {
     const bool full = (n0 + 8 <= N);
-    if (p.bias) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (full || n0 + j < N) v[j] += __ldg(p.bias + n0 + j);
+    if (bias8) {
+      if (full) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias8), b1 = *reinterpret_cast<const float4*>(bias8 + 4);
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      } else {
+        for (int j = 0; j < 8; ++j) if (n0 + j < N) v[j] += bias8[j];
+      }
     }
     if (p.act == 1) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-    }
-    if (p.gamma) {
+    } else if (p.act == 2) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) if (full || n0 + j < N) v[j] *= __ldg(p.gamma + n0 + j);
+      for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
+    }
+    if (gamma8) {
+      if (full) {
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma8), g1 = *reinterpret_cast<const float4*>(gamma8 + 4);
+        v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w; v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+      } else {
+        for (int j = 0; j < 8; ++j) if (n0 + j < N) v[j] *= gamma8[j];
+      }
     }
     const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
     if (p.residual) {
@@ -151,7 +174,7 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int b, int m, int 
       const int g = (n0 >> 2) + h;
       float x[4], dq[4];
 #pragma unroll
-      for (int d = 0; d < 4; ++d) x[d] = v[4 * h + d] + (p.bias ? __ldg(p.bias + n0 + 4 * h + d) : 0.0f);
+      for (int d = 0; d < 4; ++d) x[d] = v[4 * h + d] + (bias8 ? bias8[4 * h + d] : 0.0f);
       int idx = fsq_quantize4(p.fsq, x, dq);
       if (!valid) { idx = 0; dq[0] = dq[1] = dq[2] = dq[3] = 0.0f; }
       if (p.codes) p.codes[((long long)g * p.nb + b) * m_rows + m] = idx;
@@ -171,7 +194,7 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int b, int m, int 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float lm = v[2 * j], ph = v[2 * j + 1];
-      if (p.bias && n0 + 2 * j + 1 < N) { lm += __ldg(p.bias + n0 + 2 * j); ph += __ldg(p.bias + n0 + 2 * j + 1); }
+      if (bias8) { lm += bias8[2 * j]; ph += bias8[2 * j + 1]; }
       float mag = fminf(expf(lm), 100.0f);
       float s, c;
       sincosf(ph, &s, &c);

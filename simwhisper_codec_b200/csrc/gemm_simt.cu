@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(GemmDesc d) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int m = m0 + ty * 8 + i;
-      if (m < d.m_rows) epi_apply<KIND, TO>(d.epi, b, m, nc, d.N, d.m_rows, acc[i]);
+      if (m < d.m_rows)
+        epi_apply<KIND, TO>(d.epi, b, m, nc, d.N, d.m_rows, acc[i], d.epi.bias ? d.epi.bias + nc : nullptr,
+                            d.epi.gamma ? d.epi.gamma + nc : nullptr);
     }
   }
 }

@@ -11,8 +11,10 @@
 //              a second commit per tile publishes the TMEM accumulator)
 //   warp 2   : TMEM allocator (2 accumulator buffers of BN fp32 columns, double-buffered so the
 //              epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 4-7: epilogue      (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue of
-//              gemm.cuh -> vectorised global stores)
+//   warps 4-11: epilogue     (two warps per 32-lane TMEM group, each owning half of the BN columns:
+//              per-column bias/gamma staged once per tile in shared memory, software-pipelined
+//              tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue of gemm.cuh ->
+//              vectorised global stores)
 // Grid = min(#tiles, #SMs); tiles are walked n-fastest so concurrently resident CTAs share the A slab
 // in L2 while the whole weight matrix stays L2-resident.
 #include <cuda.h>
@@ -24,7 +26,6 @@ namespace swc {
 namespace {
 
 constexpr int BM = 128, BK = 64;
-constexpr int kThreads = 256;
 constexpr long long kSpinCycles = 4000000000LL;   // bounded mbarrier wait (~2 s): trap instead of hanging the GPU
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -132,11 +133,15 @@ struct SmemLayout {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOff = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
+  static constexpr int kVecOff = kBarOff + (2 * STAGES + 4) * 8 + 16;          // bias[2][BN], gamma[2][BN] (fp32)
+  static constexpr int kTotal = kVecOff + 4 * BN * 4 + 1024;                   // + alignment slack
+  static constexpr int kEpiWarps = BN >= 64 ? 8 : 4;                           // warps 4.. ; two per TMEM lane group
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
+  static constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
 };
 
 template <int BN, int STAGES, int KIND, typename TO>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(SmemLayout<BN, STAGES>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -146,6 +151,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = empty + STAGES;     // [2] accumulator ready
   uint64_t* tempty = tfull + 2;         // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* svec = reinterpret_cast<float*>(smem + L::kVecOff);     // [2][BN] bias, then [2][BN] gamma
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {32,64,128,256}
@@ -156,7 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], L::kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -221,32 +227,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp >= 4) {
-    const int ew = warp - 4;                 // TMEM lane group: this warp may touch lanes [32 ew, 32 ew + 32)
+  } else if (warp >= 4 && warp < 4 + L::kEpiWarps) {
+    const int ew = warp - 4;
+    const int lg = ew & 3;                   // TMEM lane group: this warp may touch lanes [32 lg, 32 lg + 32)
+    const int c_base = (ew >> 2) * L::kColsPerWarp;
+    const int etid = threadIdx.x - 128;
+    constexpr int kEpiThreads = 32 * L::kEpiWarps;
+    constexpr int kChunks = L::kColsPerWarp / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_batch;
       const int r = tile - b * tiles_per_batch;
       const int m0 = (r / p.n_tiles) * BM, n0 = (r % p.n_tiles) * BN;
+      // stage this tile's per-column vectors (overlaps the MMAs of this tile)
+      float* sb = svec + acc * BN;
+      float* sg = svec + (2 + acc) * BN;
+      for (int i = etid; i < BN; i += kEpiThreads) {
+        const int n = n0 + i;
+        sb[i] = (p.epi.bias && n < p.N) ? __ldg(p.epi.bias + n) : 0.0f;
+        sg[i] = (p.epi.gamma && n < p.N) ? __ldg(p.epi.gamma + n) : 1.0f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int m = m0 + ew * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int cb = 0; cb < BN / 32; ++cb) {
-        uint32_t rr[32];
-        tmem_ld32(taddr + cb * 32, rr);
+      const int m = m0 + lg * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + c_base;
+      uint32_t rr[2][32];
+      tmem_ld32(taddr, rr[0]);
+#pragma unroll
+      for (int cb = 0; cb < kChunks; ++cb) {
         tmem_ld_wait();
+        if (cb + 1 < kChunks) tmem_ld32(taddr + (cb + 1) * 32, rr[(cb + 1) & 1]);
         if (m < p.m_rows) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int nc = n0 + cb * 32 + j * 8;
+            const int cl = c_base + cb * 32 + j * 8;
+            const int nc = n0 + cl;
             if (nc < p.N) {
               float v[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(rr[j * 8 + q]);
-              epi_apply<KIND, TO>(p.epi, b, m, nc, p.N, p.m_rows, v);
+              for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(rr[cb & 1][j * 8 + q]);
+              epi_apply<KIND, TO>(p.epi, b, m, nc, p.N, p.m_rows, v, p.epi.bias ? sb + cl : nullptr,
+                                  p.epi.gamma ? sg + cl : nullptr);
             }
           }
         }
@@ -329,7 +352,7 @@ int launch(const GemmDesc& d, int num_sms, cudaStream_t s) {
   const long long total = (long long)p.m_tiles * p.n_tiles * p.nb;
   const int grid = (int)std::min<long long>(total, num_sms);
   ProfScope ps(KC_GEMM_TC, s);
-  kern<<<grid, kThreads, L::kTotal, s>>>(tmA, tmW, p);
+  kern<<<grid, L::kThreads, L::kTotal, s>>>(tmA, tmW, p);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -8,8 +8,9 @@ namespace swc {
 // ================================================================================================
 // LayerNorm: one warp per row; each lane owns NCH chunks of 8 contiguous channels.
 // ================================================================================================
-template <typename TI, typename TO, int NCH>
-__global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ in, TO* __restrict__ out,
+template <typename TO, int NCH>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, const float* __restrict__ delta,
+                                                        float* __restrict__ h_out, TO* __restrict__ out,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int nb,
                                                         int t_in, int t_out, const long long* __restrict__ lens) {
@@ -19,23 +20,36 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ i
   if (row >= (long long)nb * t_out) return;
   const int b = (int)(row / t_out), t = (int)(row % t_out);
   TO* o = out + row * C;
-  bool live = t < t_in;
+  const bool in_range = t < t_in;
+  bool live = in_range;
   if (live && lens) live = (long long)t < lens[b];
+  const long long irow = ((long long)b * t_in + t) * C;
+  float v[NCH][8];
+  if (in_range && (live || delta)) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int c0 = (c * 32 + lane) * 8;
+      load8(in + irow + c0, v[c]);
+      if (delta) {      // fused residual add: h <- h + delta (the GEMM that produced delta has no residual epilogue)
+        float dv[8];
+        load8(delta + irow + c0, dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[c][j] += dv[j];
+        if (h_out) store8(h_out + irow + c0, v[c]);
+      }
+    }
+  }
   if (!live) {
     float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int c = 0; c < NCH; ++c) store8(o + (c * 32 + lane) * 8, z);
     return;
   }
-  const TI* x = in + ((long long)b * t_in + t) * C;
-  float v[NCH][8];
   float sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    load8(x + (c * 32 + lane) * 8, v[c]);
+  for (int c = 0; c < NCH; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum += v[c][j];
-  }
   const float mean = warp_sum(sum) * (1.0f / C);
   float sq = 0.f;
 #pragma unroll
@@ -55,35 +69,32 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ i
   }
 }
 
-template <typename TI, typename TO>
-static int layernorm_t(const void* in, void* out, const float* g, const float* b, float eps, int nb, int t_in,
-                       int t_out, int C, const long long* lens, cudaStream_t s) {
+template <typename TO>
+static int layernorm_t(const float* in, const float* delta, float* h_out, void* out, const float* g, const float* b, float eps,
+                       int nb, int t_in, int t_out, int C, const long long* lens, cudaStream_t s) {
   const long long rows = (long long)nb * t_out;
   const int warps = 8;
   dim3 grid((unsigned)ceil_div_ll(rows, warps));
   ProfScope ps(KC_LAYERNORM, s);
-  if (C == 768) layernorm_kernel<TI, TO, 3><<<grid, warps * 32, 0, s>>>((const TI*)in, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
-  else if (C == 512) layernorm_kernel<TI, TO, 2><<<grid, warps * 32, 0, s>>>((const TI*)in, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
-  else if (C == 256) layernorm_kernel<TI, TO, 1><<<grid, warps * 32, 0, s>>>((const TI*)in, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
-  else if (C == 1024) layernorm_kernel<TI, TO, 4><<<grid, warps * 32, 0, s>>>((const TI*)in, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
+  if (C == 768) layernorm_kernel<TO, 3><<<grid, warps * 32, 0, s>>>(in, delta, h_out, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
+  else if (C == 512) layernorm_kernel<TO, 2><<<grid, warps * 32, 0, s>>>(in, delta, h_out, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
   else { set_error("layernorm: unsupported width %d", C); return -1; }
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int layernorm(const void* in, int in_type, void* out, int out_type, const float* gamma, const float* beta,
-              float eps, int nb, int t_in, int t_out, int C, const long long* lens, cudaStream_t s) {
-  if (in_type == 0 && out_type == 0) return layernorm_t<float, float>(in, out, gamma, beta, eps, nb, t_in, t_out, C, lens, s);
-  if (in_type == 0 && out_type == 1) return layernorm_t<float, bf16>(in, out, gamma, beta, eps, nb, t_in, t_out, C, lens, s);
-  set_error("layernorm: unsupported types %d->%d", in_type, out_type);
-  return -1;
+int layernorm(const float* in, const float* delta, float* h_out, void* out, int out_type, const float* gamma,
+              const float* beta, float eps, int nb, int t_in, int t_out, int C, const long long* lens, cudaStream_t s) {
+  if (out_type == 0) return layernorm_t<float>(in, delta, h_out, out, gamma, beta, eps, nb, t_in, t_out, C, lens, s);
+  return layernorm_t<bf16>(in, delta, h_out, out, gamma, beta, eps, nb, t_in, t_out, C, lens, s);
 }
 
 // ================================================================================================
 // depthwise conv k7 + bias + LayerNorm (Vocos ConvNeXt block, reference modules.py:1232-1240)
 // ================================================================================================
 template <typename TO, int NCH>
-__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ delta,
+                                                         float* __restrict__ x_out, const float* __restrict__ w,
                                                          const float* __restrict__ bias,
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float eps,
@@ -100,12 +111,19 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
   for (int k = 0; k < 7; ++k) {
     const int tt = t + k - 3;
     if (tt < 0 || tt >= T) continue;
-    const float* xr = x + ((long long)b * T + tt) * C;
+    const long long ro = ((long long)b * T + tt) * C;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int c0 = (c * 32 + lane) * 8;
       float xv[8], wv[8];
-      load8(xr + c0, xv);
+      load8(x + ro + c0, xv);
+      if (delta) {     // block input = x + delta (previous block's gamma * pwconv2 output); x_out must not alias x
+        float dv[8];
+        load8(delta + ro + c0, dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] += dv[j];
+        if (k == 3) store8(x_out + ro + c0, xv);
+      }
       load8(w + k * C + c0, wv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[c][j] = fmaf(xv[j], wv[j], v[c][j]);
@@ -136,14 +154,15 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
   }
 }
 
-int dwconv7_ln(const float* x, const float* w7c, const float* bias, const float* gamma, const float* beta,
-               float eps, void* out, int out_type, int nb, int T, int C, cudaStream_t s) {
+int dwconv7_ln(const float* x, const float* delta, float* x_out, const float* w7c, const float* bias, const float* gamma,
+               const float* beta, float eps, void* out, int out_type, int nb, int T, int C, cudaStream_t s) {
   SWC_REQUIRE(C == 512, "dwconv7_ln: only C=512 is built (got %d)", C);
+  SWC_REQUIRE(!delta || (x_out && x_out != x), "dwconv7_ln: fused residual needs a distinct output stream buffer");
   const long long rows = (long long)nb * T;
   dim3 grid((unsigned)ceil_div_ll(rows, 8));
   ProfScope ps(KC_DWCONV_LN, s);
-  if (out_type == 0) dwconv7_ln_kernel<float, 2><<<grid, 256, 0, s>>>(x, w7c, bias, gamma, beta, eps, (float*)out, nb, T);
-  else dwconv7_ln_kernel<bf16, 2><<<grid, 256, 0, s>>>(x, w7c, bias, gamma, beta, eps, (bf16*)out, nb, T);
+  if (out_type == 0) dwconv7_ln_kernel<float, 2><<<grid, 256, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (float*)out, nb, T);
+  else dwconv7_ln_kernel<bf16, 2><<<grid, 256, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (bf16*)out, nb, T);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -5,14 +5,17 @@
 
 namespace swc {
 
-// LayerNorm over the last dim (C multiple of 256, <= 1024) of channel-last rows.
+// LayerNorm over the last dim (C = 768 or 512) of channel-last fp32 rows, optionally fused with the residual
+// add that precedes it:  h' = in + delta (written to h_out, which may alias `in`), out = LN(h').
 // Output has t_out >= t_in rows per batch; rows t >= t_in or t >= lens[b] (if lens) are written as zero.
-int layernorm(const void* in, int in_type, void* out, int out_type, const float* gamma, const float* beta,
-              float eps, int nb, int t_in, int t_out, int C, const long long* lens, cudaStream_t s);
+int layernorm(const float* in, const float* delta, float* h_out, void* out, int out_type, const float* gamma,
+              const float* beta, float eps, int nb, int t_in, int t_out, int C, const long long* lens, cudaStream_t s);
 
-// Vocos ConvNeXt front half: depthwise conv k7 (pad 3) + bias + LayerNorm(eps) over C=512. x fp32 (nb,T,C).
-int dwconv7_ln(const float* x, const float* w7c /*[7][C]*/, const float* bias, const float* gamma,
-               const float* beta, float eps, void* out, int out_type, int nb, int T, int C, cudaStream_t s);
+// Vocos ConvNeXt front half: depthwise conv k7 (pad 3) + bias + LayerNorm(eps) over C=512 on x (+ delta) fp32
+// (nb,T,C).  With delta, the updated stream x + delta is also written to x_out (must not alias x).
+int dwconv7_ln(const float* x, const float* delta, float* x_out, const float* w7c /*[7][C]*/, const float* bias,
+               const float* gamma, const float* beta, float eps, void* out, int out_type, int nb, int T, int C,
+               cudaStream_t s);
 
 // Anti-aliased SnakeBeta along time of channel-last (nb,T,C): 2x up (12 taps) -> snake -> 2x down.
 int aa_snake(const void* in, int in_type, void* out, int out_type, const float* taps_up, const float* taps_dn,

@@ -54,6 +54,12 @@ def test_gemm_tcgen05_bf16(M, N, K):
     assert err < 1e-3 * max(1.0, ref.abs().max().item()), err       # fp32 accumulation of exact bf16 products
     out16 = _gemm(2, A, W, b, True)
     assert (out16.double() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+    # fused erf-GELU epilogue (tanh-form fit, 2.5e-5 + tanh.approx error) against exact GELU, bf16 output
+    gel = _gemm(2, A, W, b, True, act=2)
+    gref = torch.nn.functional.gelu(ref)
+    assert (gel.double() - gref).abs().max().item() < 1.5e-2 * max(1.0, gref.abs().max().item())
+    gel32 = _gemm(2, A, W, b, False, act=2)
+    assert (gel32.double() - gref).abs().max().item() < 2e-3 * max(1.0, gref.abs().max().item())
     # the SIMT kernel on the same bf16 operands must agree to fp32 rounding
     simt = _gemm(1, A, W, b, False)
     assert (simt.double() - out.double()).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
