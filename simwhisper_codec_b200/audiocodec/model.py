@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 import yaml
 
-from .. import _lib
+from .. import _lib, windows
 from ..weights import state_dict_schema
 
 _BUFFER_LEAVES = ("positional_embedding", "filter", "window", "dim_base_index", "num_levels")
@@ -393,78 +393,64 @@ class AudioCodec(nn.Module):
         wav, olens = self._detokenize(codes, lens)
         return {"y": wav[:, None, :], "output_length": olens}
 
+    # ---- window batches (shared by the single-GPU API below and parallel.ShardedCodec)
+    def encode_jobs(self, wav_list, jobs, device) -> torch.Tensor:
+        """Tokenize the given (item, start, n_valid) windows as one batch -> codes (8, len(jobs), 375) int32."""
+        if not jobs:
+            return torch.zeros((self.num_groups, 0, 375), dtype=torch.int32, device=device)
+        width = max(j.n_valid for j in jobs)
+        x = torch.zeros((len(jobs), width), dtype=torch.float32, device=device)
+        for k, j in enumerate(jobs):
+            w = torch.as_tensor(wav_list[j.item])
+            x[k, : j.n_valid] = w[j.start:j.start + j.n_valid].to(device=device, dtype=torch.float32, non_blocking=True)
+        wl = torch.tensor([j.n_valid for j in jobs], dtype=torch.int64).to(device, non_blocking=True)
+        return self._tokenize(x, wl, want_zq=False)[0]
+
+    def decode_jobs(self, codes_list, jobs, device) -> torch.Tensor:
+        """Detokenize decode windows that share one pad length T' -> wav (len(jobs), 1280 T')."""
+        Tp = jobs[0].pad_len
+        ct = torch.zeros((self.num_groups, len(jobs), Tp), dtype=torch.int64, device=device)
+        for k, j in enumerate(jobs):
+            ct[:, k, : j.n_valid] = torch.as_tensor(codes_list[j.item])[:, j.start:j.start + j.n_valid].to(
+                device=device, dtype=torch.int64, non_blocking=True)
+        cl = torch.tensor([j.n_valid for j in jobs], dtype=torch.int64).to(device, non_blocking=True)
+        return self._detokenize(ct, cl)[0]
+
     @torch.inference_mode()
     def encode(self, wav_list, overlap_seconds=10, device=torch.device("cuda")):
-        """reference model.py:244-308: 30-s windows every (30-overlap) s, first (30-overlap) s of codes kept."""
+        """reference model.py:244-308: 30-s windows every (30-overlap) s, first (30-overlap) s of codes kept.
+        All (item, window) pairs run as one batch; stitching is a single gather (windows.py)."""
         device = torch.device(device)
-        sr, rate = self.input_sample_rate, self.encoder_downsample_rate
-        win = int(self.max_audio_seconds * sr)
-        hop = int((self.max_audio_seconds - overlap_seconds) * sr)
-        keep = hop // rate
-        B = len(wav_list)
         lens = [int(len(w)) for w in wav_list]
-        jobs = []                                           # (item, start, n_valid)
-        for i, L in enumerate(lens):
-            for c in range((L + hop - 1) // hop if hop > 0 else 0):
-                jobs.append((i, c * hop, min(L - c * hop, win)))
+        jobs = windows.plan_encode(lens, overlap_seconds, self.input_sample_rate, self.max_audio_seconds)
         if not jobs:
-            return {"codes_list": [torch.zeros(self.num_groups, 0, device=device, dtype=torch.long) for _ in range(B)]}
-        N = len(jobs)
-        width = max(n for _, _, n in jobs)
-        x = torch.zeros((N, width), dtype=torch.float32, device=device)
-        for j, (i, s, n) in enumerate(jobs):
-            x[j, :n] = wav_list[i][s:s + n].to(device=device, dtype=torch.float32, non_blocking=True)
-        wl = torch.tensor([n for _, _, n in jobs], dtype=torch.int64).to(device, non_blocking=True)
-        codes, _, _ = self._tokenize(x, wl, want_zq=False)                     # (8, N, 375)
-        # stitch with one gather: output position p of item i <- window (i, p // keep), frame p % keep
-        src, splits = [], []
-        first_job = {}
-        for j, (i, s, n) in enumerate(jobs):
-            first_job.setdefault(i, j)
-        for i, L in enumerate(lens):
-            n_codes = L // rate
-            splits.append(n_codes)
-            if n_codes:
-                p = torch.arange(n_codes, dtype=torch.int64)
-                src.append((first_job[i] + p // keep) * 375 + p % keep)
-        flat = codes.reshape(self.num_groups, N * 375)
-        if src:
-            out = flat.index_select(1, torch.cat(src).to(device, non_blocking=True))
-        else:
-            out = flat[:, :0]
-        return {"codes_list": list(torch.split(out, splits, dim=1))}
+            return {"codes_list": [torch.zeros(self.num_groups, 0, device=device, dtype=torch.long) for _ in lens]}
+        codes = self.encode_jobs(wav_list, jobs, device)                       # (8, N, 375)
+        return {"codes_list": self.stitch_codes(codes, lens, jobs, overlap_seconds)}
+
+    def stitch_codes(self, codes, lens, jobs, overlap_seconds):
+        src, splits = windows.encode_gather_index(lens, jobs, overlap_seconds, self.input_sample_rate,
+                                                  self.max_audio_seconds, self.encoder_downsample_rate)
+        flat = codes.reshape(self.num_groups, -1)
+        idx = torch.tensor(src, dtype=torch.int64).to(codes.device, non_blocking=True)
+        return list(torch.split(flat.index_select(1, idx), splits, dim=1))
 
     @torch.inference_mode()
     def decode(self, codes_list, overlap_seconds=10, device=torch.device("cuda")):
-        """reference model.py:310-373: windows of <=375 codes every 250; the pad length T' of window index c
-        is the batch maximum min(375, maxlen-250c), exactly as the reference's un-padded decode batches."""
+        """reference model.py:310-373: windows of <=375 codes every 250; the pad length T' of window index c is the
+        batch maximum min(375, maxlen-250c), exactly as the reference's un-padded decode batches."""
         device = torch.device(device)
-        sr, rate = self.input_sample_rate, self.encoder_downsample_rate
-        win = int(self.max_audio_seconds * sr // rate)
-        keep = int((self.max_audio_seconds - overlap_seconds) * sr // rate)
-        up = self.decoder_upsample_rate
-        B = len(codes_list)
         lens = [int(c.shape[-1]) for c in codes_list]
-        maxlen = max(lens) if lens else 0
+        up = self.decoder_upsample_rate
         outs = [torch.empty(L * up, dtype=torch.float32, device=device) for L in lens]
-        n_chunks = (maxlen + keep - 1) // keep if keep > 0 else 0
-        groups: Dict[int, list] = {}                         # T' -> [(item, chunk, n_valid)]
-        for c in range(n_chunks):
-            Tp = min(c * keep + win, maxlen) - c * keep
-            for i, L in enumerate(lens):
-                n = min(max(L - c * keep, 0), Tp)
-                if n > 0:
-                    groups.setdefault(Tp, []).append((i, c, n))
-        for Tp, jobs in groups.items():
-            N = len(jobs)
-            ct = torch.zeros((self.num_groups, N, Tp), dtype=torch.int64, device=device)
-            for j, (i, c, n) in enumerate(jobs):
-                ct[:, j, :n] = codes_list[i][:, c * keep:c * keep + n].to(device=device, dtype=torch.int64, non_blocking=True)
-            cl = torch.tensor([n for _, _, n in jobs], dtype=torch.int64).to(device, non_blocking=True)
-            wav, _ = self._detokenize(ct, cl)
-            for j, (i, c, n) in enumerate(jobs):
-                m = min(n, keep) * up
-                outs[i][c * keep * up:c * keep * up + m] = wav[j, :m]
+        groups = windows.plan_decode(lens, overlap_seconds, self.input_sample_rate, self.max_audio_seconds,
+                                     self.encoder_downsample_rate)
+        for _, jobs in groups.items():
+            wav = self.decode_jobs(codes_list, jobs, device)
+            for k, j in enumerate(jobs):
+                off, n = windows.decode_keep(j, overlap_seconds, self.input_sample_rate, self.max_audio_seconds,
+                                             self.encoder_downsample_rate, up)
+                outs[j.item][off:off + n] = wav[k, :n]
         return {"syn_wav_list": outs}
 
     @classmethod
