@@ -105,7 +105,7 @@ def _worker(rank, world, port, lens, q):
     codes = sc.encode(wavs, device="cpu")["codes_list"]
     wav = sc.decode(codes, device="cpu")["syn_wav_list"]
     if rank == 0:
-        q.put(([c.clone() for c in codes], [w.clone() for w in wav]))
+        q.put(([c.numpy().copy() for c in codes], [w.numpy().copy() for w in wav]))  # numpy: pickled by value
     dist.barrier()
     dist.destroy_process_group()
 
@@ -121,6 +121,8 @@ def test_sharded_equals_single_process_gloo():
     for p in procs:
         p.start()
     codes2, wav2 = q.get(timeout=120)
+    codes2 = [torch.from_numpy(c) for c in codes2]
+    wav2 = [torch.from_numpy(w) for w in wav2]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
