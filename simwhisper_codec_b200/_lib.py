@@ -44,6 +44,7 @@ SIGNATURES = {
     "swc_profile": (None, [_i]),
     "swc_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(_i64), _i]),
     "swc_test_gemm": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "swc_set_gemm_variant": (None, [_i]),
     "swc_test_attention": (_i, [_i, _p, _p, _p, _i, _i, _i, _p]),
 }
 

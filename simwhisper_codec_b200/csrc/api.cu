@@ -362,8 +362,15 @@ int swc_test_gemm(int backend, const void* A, const void* W, const float* bias, 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return gemm_tc(d, EPI_STORE, out_bf16, sms, (cudaStream_t)stream);
+  // 2: first-generation kernel, 3: TMA-store epilogue, 4: CTA pairs + TMA-store epilogue
+  const int saved = get_gemm_variant();
+  set_gemm_variant(backend - 2);
+  const int rc = gemm_tc(d, EPI_STORE, out_bf16, sms, (cudaStream_t)stream);
+  set_gemm_variant(saved);
+  return rc;
 }
+
+void swc_set_gemm_variant(int variant) { set_gemm_variant(variant); }
 
 int swc_test_attention(int backend, const void* qkv, void* out, const int64_t* lens, int batch, int T, int heads, void* stream) {
   if (backend == 0) return attention_simt(qkv, 0, out, (const long long*)lens, batch, T, heads, (cudaStream_t)stream);

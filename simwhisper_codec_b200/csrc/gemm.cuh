@@ -209,5 +209,11 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int b, int m, int 
 // type codes: 0 = fp32, 1 = bf16
 int gemm_simt(const GemmDesc& d, int kind, int a_type, int out_type, cudaStream_t s);
 int gemm_tc(const GemmDesc& d, int kind, int out_type, int num_sms, cudaStream_t s);
+// second-generation tcgen05 kernel (gemm_tc2.cu): CTA-pair MMA + TMA-store epilogue for plain EPI_STORE problems.
+// variant 0 = first-generation kernel only, 1 = single-CTA tiles + TMA store, 2 = CTA pairs (default).
+bool gemm_tc2_eligible(const GemmDesc& d);
+int gemm_tc2(const GemmDesc& d, int out_type, int num_sms, int variant, cudaStream_t s);
+void set_gemm_variant(int v);
+int get_gemm_variant();
 
 }  // namespace swc

@@ -18,6 +18,7 @@
 // Grid = min(#tiles, #SMs); tiles are walked n-fastest so concurrently resident CTAs share the A slab
 // in L2 while the whole weight matrix stays L2-resident.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "gemm.cuh"
 
@@ -366,7 +367,18 @@ int launch_bn(const GemmDesc& d, int num_sms, cudaStream_t s) {
 
 }  // namespace
 
+static int g_gemm_variant = -1;
+void set_gemm_variant(int v) { g_gemm_variant = v; }
+int get_gemm_variant() {
+  if (g_gemm_variant < 0) {
+    const char* e = getenv("SWC_GEMM_VARIANT");
+    g_gemm_variant = e ? atoi(e) : 2;
+  }
+  return g_gemm_variant;
+}
+
 int gemm_tc(const GemmDesc& d, int kind, int out_type, int num_sms, cudaStream_t s) {
+  if (kind == EPI_STORE && get_gemm_variant() > 0 && gemm_tc2_eligible(d)) return gemm_tc2(d, out_type, num_sms, get_gemm_variant(), s);
   SWC_REQUIRE(d.tap_k % BK == 0 && d.n_taps >= 1 && d.n_taps <= kMaxTaps, "gemm_tc: tap_k=%d must be a multiple of 64 (taps=%d)", d.tap_k, d.n_taps);
   SWC_REQUIRE(d.m_rows > 0 && d.nb > 0 && d.N > 0, "gemm_tc: empty problem");
   SWC_REQUIRE(((uintptr_t)d.A & 15) == 0 && ((uintptr_t)d.W & 15) == 0, "gemm_tc: operands must be 16-byte aligned");

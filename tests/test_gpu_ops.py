@@ -43,19 +43,22 @@ def test_gemm_simt_fp32(M, N, K):
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (300, 768, 768), (1000, 2304, 768), (257, 32, 512),
                                    (130, 656, 512), (4096, 4096, 512), (515, 512, 4096), (20000, 3072, 768)])
-def test_gemm_tcgen05_bf16(M, N, K):
+@pytest.mark.parametrize("backend", [2, 3, 4])
+def test_gemm_tcgen05_bf16(M, N, K, backend):
+    """backend 2 = first-generation kernel, 3 = TMA-store epilogue, 4 = CTA-pair MMA (shapes the second generation
+    does not take fall back to the first)."""
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
     W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
     b = torch.randn(N, device="cuda", generator=g)
     ref = A.double() @ W.double().T + b.double()
-    out = _gemm(2, A, W, b, False)
+    out = _gemm(backend, A, W, b, False)
     err = (out.double() - ref).abs().max().item()
     assert err < 1e-3 * max(1.0, ref.abs().max().item()), err       # fp32 accumulation of exact bf16 products
-    out16 = _gemm(2, A, W, b, True)
+    out16 = _gemm(backend, A, W, b, True)
     assert (out16.double() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
     # fused erf-GELU epilogue (tanh-form fit, 2.5e-5 + tanh.approx error) against exact GELU, bf16 output
-    gel = _gemm(2, A, W, b, True, act=2)
+    gel = _gemm(backend, A, W, b, True, act=2)
     gref = torch.nn.functional.gelu(ref)
     assert (gel.double() - gref).abs().max().item() < 1.5e-2 * max(1.0, gref.abs().max().item())
     gel32 = _gemm(2, A, W, b, False, act=2)
