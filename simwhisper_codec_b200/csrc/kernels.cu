@@ -91,66 +91,136 @@ int layernorm(const float* in, const float* delta, float* h_out, void* out, int 
 
 // ================================================================================================
 // depthwise conv k7 + bias + LayerNorm (Vocos ConvNeXt block, reference modules.py:1232-1240)
+//
+// HBM-streaming: every element of x (and delta) is read once (+ 6 halo rows per strip), x + delta and the
+// normalised row are written once.  One block = 128 threads = the 512 channels (4 per thread) of one time strip
+// of one item; it slides along time with a 14-row register window of s = x + delta, producing 8 output rows per
+// step: 16 independent 16-byte loads in flight per thread, the 7-tap convolution entirely in registers, and the
+// LayerNorm statistics (two-pass, as torch) reduced across the 4 warps through shared memory once per 8 rows.
 // ================================================================================================
-template <typename TO, int NCH>
-__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ delta,
-                                                         float* __restrict__ x_out, const float* __restrict__ w,
-                                                         const float* __restrict__ bias,
-                                                         const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, float eps,
-                                                         TO* __restrict__ out, int nb, int T) {
-  constexpr int C = NCH * 256;
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= (long long)nb * T) return;
-  const int b = (int)(row / T), t = (int)(row % T);
-  float v[NCH][8];
+constexpr int kDwRows = 8;       // output rows per step
+constexpr int kDwThreads = 128;  // 4 channels per thread, C = 512
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_fma(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename TO, bool HAS_DELTA>
+__global__ void __launch_bounds__(kDwThreads) dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ delta,
+                                                                float* __restrict__ x_out, const float* __restrict__ w,
+                                                                const float* __restrict__ bias,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps,
+                                                                TO* __restrict__ out, int T, int strip) {
+  constexpr int C = 512, R = kDwRows;
+  __shared__ __align__(16) float red_sum[R][4];
+  __shared__ __align__(16) float red_sq[R][4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c0 = tid * 4;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * strip;
+  const int t_end = min(T, t0 + strip);
+  const float* xb = x + (long long)b * T * C + c0;
+  const float* db = HAS_DELTA ? delta + (long long)b * T * C + c0 : nullptr;
+  float* xo = HAS_DELTA ? x_out + (long long)b * T * C + c0 : nullptr;
+  TO* ob = out + (long long)b * T * C + c0;
+
+  float4 wk[7];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) load8(bias + (c * 32 + lane) * 8, v[c]);
-#pragma unroll
-  for (int k = 0; k < 7; ++k) {
-    const int tt = t + k - 3;
-    if (tt < 0 || tt >= T) continue;
-    const long long ro = ((long long)b * T + tt) * C;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int c0 = (c * 32 + lane) * 8;
-      float xv[8], wv[8];
-      load8(x + ro + c0, xv);
-      if (delta) {     // block input = x + delta (previous block's gamma * pwconv2 output); x_out must not alias x
-        float dv[8];
-        load8(delta + ro + c0, dv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xv[j] += dv[j];
-        if (k == 3) store8(x_out + ro + c0, xv);
-      }
-      load8(w + k * C + c0, wv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[c][j] = fmaf(xv[j], wv[j], v[c][j]);
+  for (int k = 0; k < 7; ++k) wk[k] = *reinterpret_cast<const float4*>(w + k * C + c0);
+  const float4 bs = *reinterpret_cast<const float4*>(bias + c0);
+  const float4 gm = *reinterpret_cast<const float4*>(gamma + c0);
+  const float4 bt = *reinterpret_cast<const float4*>(beta + c0);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // window[j] holds s(row base - 3 + j); rows outside [0, T) are the convolution's zero padding
+  float4 win[R + 6];
+  auto load_row = [&](int t, bool own) -> float4 {
+    if (t < 0 || t >= T) return zero4;
+    float4 v = *reinterpret_cast<const float4*>(xb + (long long)t * C);
+    if (HAS_DELTA) {
+      v = f4_add(v, *reinterpret_cast<const float4*>(db + (long long)t * C));
+      if (own) *reinterpret_cast<float4*>(xo + (long long)t * C) = v;   // the updated residual stream, written by the strip that owns the row
     }
-  }
-  float sum = 0.f;
+    return v;
+  };
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
+  for (int j = 0; j < 6; ++j) win[j] = load_row(t0 - 3 + j, j >= 3);
+
+  for (int base = t0; base < t_end; base += R) {
+    // rows base+3 .. base+10 (the last three of the strip's final step belong to the next strip)
+    float4 xv[R], dv[R];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sum += v[c][j];
-  const float mean = warp_sum(sum) * (1.0f / C);
-  float sq = 0.f;
+    for (int j = 0; j < R; ++j) {
+      const int t = base + 3 + j;
+      const bool ok = t < T;
+      xv[j] = ok ? *reinterpret_cast<const float4*>(xb + (long long)t * C) : zero4;
+      if (HAS_DELTA) dv[j] = ok ? *reinterpret_cast<const float4*>(db + (long long)t * C) : zero4;
+    }
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
+    for (int j = 0; j < R; ++j) {
+      const int t = base + 3 + j;
+      float4 v = xv[j];
+      if (HAS_DELTA) {
+        v = f4_add(v, dv[j]);
+        if (t < t_end) *reinterpret_cast<float4*>(xo + (long long)t * C) = v;
+      }
+      win[6 + j] = v;
+    }
+    // conv + bias for rows base .. base+7
+    float4 y[R];
+    float psum[R];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { float dlt = v[c][j] - mean; sq = fmaf(dlt, dlt, sq); }
-  const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / C) + eps);
-  TO* o = out + row * C;
+    for (int r = 0; r < R; ++r) {
+      float4 a = bs;
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int c0 = (c * 32 + lane) * 8;
-    float g[8], bt[8], r[8];
-    load8(gamma + c0, g);
-    load8(beta + c0, bt);
+      for (int k = 0; k < 7; ++k) a = f4_fma(win[r + k], wk[k], a);
+      y[r] = a;
+      psum[r] = warp_sum((a.x + a.y) + (a.z + a.w));
+    }
+    if (lane == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = (v[c][j] - mean) * rstd * g[j] + bt[j];
-    store8(o + c0, r);
+      for (int r = 0; r < R; ++r) red_sum[r][warp] = psum[r];
+    }
+    __syncthreads();
+    float mean[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float4 p = *reinterpret_cast<const float4*>(red_sum[r]);
+      mean[r] = ((p.x + p.y) + (p.z + p.w)) * (1.0f / C);
+      const float dx = y[r].x - mean[r], dy = y[r].y - mean[r], dz = y[r].z - mean[r], dw = y[r].w - mean[r];
+      psum[r] = warp_sum(fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw));
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) red_sq[r][warp] = psum[r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = base + r;
+      if (t < t_end) {
+        const float4 p = *reinterpret_cast<const float4*>(red_sq[r]);
+        const float rstd = 1.0f / sqrtf(((p.x + p.y) + (p.z + p.w)) * (1.0f / C) + eps);
+        float4 o;
+        o.x = (y[r].x - mean[r]) * rstd * gm.x + bt.x;
+        o.y = (y[r].y - mean[r]) * rstd * gm.y + bt.y;
+        o.z = (y[r].z - mean[r]) * rstd * gm.z + bt.z;
+        o.w = (y[r].w - mean[r]) * rstd * gm.w + bt.w;
+        store4(ob + (long long)t * C, o);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) win[j] = win[j + R];
   }
 }
 
@@ -158,11 +228,17 @@ int dwconv7_ln(const float* x, const float* delta, float* x_out, const float* w7
                const float* beta, float eps, void* out, int out_type, int nb, int T, int C, cudaStream_t s) {
   SWC_REQUIRE(C == 512, "dwconv7_ln: only C=512 is built (got %d)", C);
   SWC_REQUIRE(!delta || (x_out && x_out != x), "dwconv7_ln: fused residual needs a distinct output stream buffer");
-  const long long rows = (long long)nb * T;
-  dim3 grid((unsigned)ceil_div_ll(rows, 8));
+  // strips of 128 rows (4.7 % halo re-reads) when that still gives every SM several blocks, else 32
+  const int strip = ((long long)nb * ceil_div(T, 128) >= 4 * 148) ? 128 : 32;
+  dim3 grid(ceil_div(T, strip), nb);
   ProfScope ps(KC_DWCONV_LN, s);
-  if (out_type == 0) dwconv7_ln_kernel<float, 2><<<grid, 256, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (float*)out, nb, T);
-  else dwconv7_ln_kernel<bf16, 2><<<grid, 256, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (bf16*)out, nb, T);
+  if (out_type == 0) {
+    if (delta) dwconv7_ln_kernel<float, true><<<grid, kDwThreads, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (float*)out, T, strip);
+    else dwconv7_ln_kernel<float, false><<<grid, kDwThreads, 0, s>>>(x, nullptr, nullptr, w7c, bias, gamma, beta, eps, (float*)out, T, strip);
+  } else {
+    if (delta) dwconv7_ln_kernel<bf16, true><<<grid, kDwThreads, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (bf16*)out, T, strip);
+    else dwconv7_ln_kernel<bf16, false><<<grid, kDwThreads, 0, s>>>(x, nullptr, nullptr, w7c, bias, gamma, beta, eps, (bf16*)out, T, strip);
+  }
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
