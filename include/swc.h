@@ -132,7 +132,7 @@ int swc_test_gemm(int backend /*0 simt fp32, 1 simt bf16, 2 tcgen05 bf16 (gen 1)
                   const float* bias, void* out, int out_bf16, int M, int N, int K, int act, void* stream);
 /* tuning hook: which tcgen05 GEMM generation the pipeline uses (0 gen 1, 1 gen 2 single-CTA, 2 gen 2 CTA pairs = default) */
 void swc_set_gemm_variant(int variant);
-int swc_test_attention(int backend /*0 simt fp32, 1 simt bf16, 2 mma bf16*/, const void* qkv, void* out,
+int swc_test_attention(int backend /*0 simt fp32, 1 simt bf16, 2 mma.sync bf16, 3 tcgen05 bf16*/, const void* qkv, void* out,
                        const int64_t* lens, int batch, int T, int heads, void* stream);
 
 #ifdef __cplusplus

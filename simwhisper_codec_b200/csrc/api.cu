@@ -375,7 +375,11 @@ void swc_set_gemm_variant(int variant) { set_gemm_variant(variant); }
 int swc_test_attention(int backend, const void* qkv, void* out, const int64_t* lens, int batch, int T, int heads, void* stream) {
   if (backend == 0) return attention_simt(qkv, 0, out, (const long long*)lens, batch, T, heads, (cudaStream_t)stream);
   if (backend == 1) return attention_simt(qkv, 1, out, (const long long*)lens, batch, T, heads, (cudaStream_t)stream);
-  return attention_mma((const bf16*)qkv, (bf16*)out, (const long long*)lens, batch, T, heads, (cudaStream_t)stream);
+  if (backend == 2) return attention_mma((const bf16*)qkv, (bf16*)out, (const long long*)lens, batch, T, heads, (cudaStream_t)stream);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return attention_tc((const bf16*)qkv, (bf16*)out, (const long long*)lens, batch, T, heads, sms, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,348 @@
+// bf16 flash attention on tcgen05 (reference audiocodec/nn/modules.py:145-187): non-causal, head_dim 64, keys >=
+// lens[b] masked, q pre-scaled by the packed q_proj.  Persistent, warp-specialised, two 128-query tiles per work item:
+//
+//   warp 0      TMA producer: Q tiles (once per item) and a 3-stage ring of K|V tiles (128 keys x 64 x bf16 each)
+//   warp 1      MMA issuer (one lane) + TMEM allocator
+//                 S_i = Q_i K_j^T   UMMA M128 N128 K16 x4, both operands K-major from shared memory -> TMEM (fp32)
+//                 O_i += P_i V_j    UMMA M128 N64  K16 x8, A = P_i (bf16) from TMEM, B = V_j MN-major from shared memory
+//   warps 2-5   softmax warpgroup of query tile 0 (one thread = one query row = one TMEM lane)
+//   warps 6-9   softmax warpgroup of query tile 1
+//
+// The two tiles ping-pong: while one warpgroup exponentiates S_i(j) the tensor core computes S_{1-i} / P V of the other.
+// Per tile and key block a softmax thread reads its 128 scores from TMEM, takes the row maximum, and only when the
+// maximum grew by more than 2^8 rescales its O row in TMEM (lazy rescale: the stale maximum is used otherwise, so
+// probabilities stay <= 256 and the final 1/l normalisation is exact); it then writes P as packed bf16 back to TMEM.
+// TMEM columns: S0 0-127 | S1 128-255 | P0 256-319 | P1 320-383 | O0 384-447 | O1 448-511.
+#include <algorithm>
+
+#include "kernels.cuh"
+#include "tc_ptx.cuh"
+
+namespace swc {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int QT = 128, KT = 128, HD = 64, STAGES = 3;
+constexpr int kThreads = 320;
+constexpr int kTileBytes = 128 * 64 * 2;                 // 16 KB: Q, K or V tile
+constexpr int kQOff = 0, kKVOff = 2 * kTileBytes;
+constexpr int kBarOff = kKVOff + STAGES * 2 * kTileBytes;
+constexpr int kNumBars = 2 + 2 + 2 * STAGES + 2 + 2 + 2 + 2 + 2;
+constexpr int kSmemBytes = kBarOff + kNumBars * 8 + 16 + 1024;
+constexpr uint32_t kColS = 0, kColP = 256, kColO = 384;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;                // log2 units
+
+struct AttnParams {
+  const long long* lens;
+  bf16* out;
+  int T, H, nb, n_qp, n_items;
+};
+
+struct Item {
+  int b, h, q0, len, n_act, n_kt;
+  bool dead;
+};
+__device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
+  Item it;
+  const int qp = item % p.n_qp;
+  const int r = item / p.n_qp;
+  it.h = r % p.H;
+  it.b = r / p.H;
+  it.q0 = qp * 2 * QT;
+  long long l = p.lens ? p.lens[it.b] : p.T;
+  it.len = (int)(l > p.T ? p.T : (l < 0 ? 0 : l));
+  it.dead = it.q0 >= it.len;
+  it.n_act = (it.q0 + QT < it.len) ? 2 : 1;
+  it.n_kt = (it.len + KT - 1) / KT;
+  return it;
+}
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
+  uint64_t* q_full = bars;               // [2]
+  uint64_t* q_empty = q_full + 2;        // [2]
+  uint64_t* kv_full = q_empty + 2;       // [STAGES]
+  uint64_t* kv_empty = kv_full + STAGES; // [STAGES]
+  uint64_t* s_full = kv_empty + STAGES;  // [2] S_i written by the tensor core
+  uint64_t* s_free = s_full + 2;         // [2] S_i copied to registers by its warpgroup (4 warps)
+  uint64_t* p_full = s_free + 2;         // [2] P_i (and any O_i rescale) written by the warpgroup
+  uint64_t* o_done = p_full + 2;         // [2] P_i V accumulated
+  uint64_t* o_free = o_done + 2;         // [2] final O_i copied to registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQKV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4); mbar_init(&o_done[i], 1); mbar_init(&o_free[i], 4);
+    }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int D3 = 3 * p.H * HD;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t q_cnt[2] = {0, 0};
+      uint32_t kv_it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        if (it.dead) continue;
+        const int row0 = it.b * p.T;
+        for (int i = 0; i < it.n_act; ++i) {
+          mbar_wait(&q_empty[i], (q_cnt[i] & 1) ^ 1);
+          mbar_expect_tx(&q_full[i], kTileBytes);
+          tma_load_2d<1>(&tmQKV, smem_u32(&q_full[i]), smem + kQOff + i * kTileBytes, it.h * HD, row0 + it.q0 + i * QT);
+          ++q_cnt[i];
+        }
+        for (int j = 0; j < it.n_kt; ++j, ++kv_it) {
+          const uint32_t st = kv_it % STAGES, ph = (kv_it / STAGES) & 1;
+          mbar_wait(&kv_empty[st], ph ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * kTileBytes);
+          uint8_t* dst = smem + kKVOff + st * 2 * kTileBytes;
+          tma_load_2d<1>(&tmQKV, smem_u32(&kv_full[st]), dst, (p.H + it.h) * HD, row0 + j * KT);
+          tma_load_2d<1>(&tmQKV, smem_u32(&kv_full[st]), dst + kTileBytes, (2 * p.H + it.h) * HD, row0 + j * KT);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(QT, KT);          // Q K^T: both K-major
+      constexpr uint32_t idesc_o = make_idesc(QT, HD, 1);       // P V: B = V is MN-major ([key][dim], dim contiguous)
+      uint32_t q_cnt[2] = {0, 0}, s_cnt[2] = {0, 0}, pv_cnt[2] = {0, 0}, item_cnt[2] = {0, 0};
+      uint32_t kv_it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        if (it.dead) continue;
+        auto issue_s = [&](int i, uint32_t st, bool last) {
+          mbar_wait(&s_free[i], (s_cnt[i] & 1) ^ 1);            // the previous S_i has been copied out
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(smem + kQOff + i * kTileBytes));
+          const uint64_t bdesc = make_smem_desc(smem_u32(smem + kKVOff + st * 2 * kTileBytes));
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) umma_bf16<1>(tmem_base + kColS + i * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+          umma_commit<1>(&s_full[i]);
+          if (last) umma_commit<1>(&q_empty[i]);
+          ++s_cnt[i];
+        };
+        for (int i = 0; i < it.n_act; ++i) { mbar_wait(&q_full[i], q_cnt[i] & 1); ++q_cnt[i]; }
+        {
+          const uint32_t st = kv_it % STAGES, ph = (kv_it / STAGES) & 1;
+          mbar_wait(&kv_full[st], ph);
+          tc_fence_after();
+          for (int i = 0; i < it.n_act; ++i) issue_s(i, st, it.n_kt == 1);
+        }
+        for (int j = 0; j < it.n_kt; ++j, ++kv_it) {
+          const uint32_t st = kv_it % STAGES;
+          for (int i = 0; i < it.n_act; ++i) {
+            if (j + 1 < it.n_kt) {
+              const uint32_t st1 = (kv_it + 1) % STAGES, ph1 = ((kv_it + 1) / STAGES) & 1;
+              if (i == 0) { mbar_wait(&kv_full[st1], ph1); tc_fence_after(); }
+              issue_s(i, st1, j + 2 == it.n_kt);
+            }
+            mbar_wait(&p_full[i], pv_cnt[i] & 1);
+            if (j == 0) mbar_wait(&o_free[i], (item_cnt[i] & 1) ^ 1);   // the previous item's O_i has been read
+            tc_fence_after();
+            const uint32_t vaddr = smem_u32(smem + kKVOff + st * 2 * kTileBytes + kTileBytes);
+#pragma unroll
+            for (int k = 0; k < KT / 16; ++k) {
+              // A: 16 keys = 8 packed columns of P_i; B: 16 key rows of V = 2 swizzle atoms of 8 rows x 128 B
+              umma_bf16_ts(tmem_base + kColO + i * 64, tmem_base + kColP + i * 64 + k * 8, make_smem_desc(vaddr + k * 2048), idesc_o,
+                           (j | k) != 0);
+            }
+            umma_commit<1>(&o_done[i]);
+            ++pv_cnt[i];
+          }
+          umma_commit<1>(&kv_empty[st]);
+        }
+        for (int i = 0; i < it.n_act; ++i) ++item_cnt[i];
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int i = (warp - 2) >> 2;                    // query tile of this warpgroup
+    const int lg = warp & 3;                          // TMEM lane group this warp may access
+    const int row = lg * 32 + lane;                   // query row inside the tile
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    const int DO = p.H * HD;
+    uint32_t s_cnt = 0, o_cnt = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const Item it = decode_item(p, item);
+      const int q = it.q0 + i * QT + row;
+      bf16* orow = p.out + ((long long)it.b * p.T + q) * DO + it.h * HD;
+      if (it.dead || i >= it.n_act) {                 // tile of padded queries: defined zero output
+        if (q < p.T) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
+        }
+        continue;
+      }
+      float m_used = -INFINITY, l = 0.f;
+      for (int j = 0; j < it.n_kt; ++j) {
+        mbar_wait(&s_full[i], s_cnt & 1);
+        ++s_cnt;
+        tc_fence_after();
+        uint32_t s[128];
+        {
+          uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+          uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+          const uint32_t sa = lane_addr + kColS + i * 128;
+          tmem_ld32(sa, s0); tmem_ld32(sa + 32, s1); tmem_ld32(sa + 64, s2); tmem_ld32(sa + 96, s3);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[i]);
+        const int valid = it.len - j * KT;             // > 0
+        if (valid < KT) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) if (c >= valid) s[c] = 0xff800000u;   // -inf
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 128; c += 4) {
+          mx[0] = fmaxf(mx[0], __uint_as_float(s[c])); mx[1] = fmaxf(mx[1], __uint_as_float(s[c + 1]));
+          mx[2] = fmaxf(mx[2], __uint_as_float(s[c + 2])); mx[3] = fmaxf(mx[3], __uint_as_float(s[c + 3]));
+        }
+        const float mxl = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kLog2e;
+        float scale = 1.0f;
+        const bool grow = mxl > m_used + kRescaleThreshold;     // always true for j == 0 (m_used = -inf)
+        if (grow) { scale = ex2(m_used - mxl); m_used = mxl; }   // j == 0: scale = 0, l = 0, O not yet written
+        float sum[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[64];
+#pragma unroll
+        for (int c = 0; c < 128; c += 4) {
+          const float p0 = ex2(fmaf(__uint_as_float(s[c]), kLog2e, -m_used));
+          const float p1 = ex2(fmaf(__uint_as_float(s[c + 1]), kLog2e, -m_used));
+          const float p2 = ex2(fmaf(__uint_as_float(s[c + 2]), kLog2e, -m_used));
+          const float p3 = ex2(fmaf(__uint_as_float(s[c + 3]), kLog2e, -m_used));
+          sum[0] += p0; sum[1] += p1; sum[2] += p2; sum[3] += p3;
+          pk[c >> 1] = pack2(p0, p1);
+          pk[(c >> 1) + 1] = pack2(p2, p3);
+        }
+        l = fmaf(l, scale, (sum[0] + sum[1]) + (sum[2] + sum[3]));
+        if (j > 0) {
+          mbar_wait(&o_done[i], o_cnt & 1);             // P_i(j-1) V accumulated: P_i is free, O_i is stable
+          ++o_cnt;
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, grow)) {
+            const uint32_t oa = lane_addr + kColO + i * 64;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t o[32];
+              tmem_ld32(oa + half * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * scale);
+              tmem_st32(oa + half * 32, o);
+            }
+          }
+        }
+        {
+          const uint32_t pa = lane_addr + kColP + i * 64;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t(&chunk)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]);
+            tmem_st16(pa + c * 16, chunk);
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[i]);
+      }
+      // ---- final: O_i / l -> bf16 rows
+      mbar_wait(&o_done[i], o_cnt & 1);
+      ++o_cnt;
+      tc_fence_after();
+      uint32_t o[64];
+      {
+        uint32_t(&o0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&o[0]);
+        uint32_t(&o1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&o[32]);
+        const uint32_t oa = lane_addr + kColO + i * 64;
+        tmem_ld32(oa, o0); tmem_ld32(oa + 32, o1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[i]);
+      const float inv = (q < it.len && l > 0.f) ? 1.0f / l : 0.f;     // padded query rows -> 0
+      if (q < p.T) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 u;
+          u.x = pack2(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
+          u.y = pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
+          u.z = pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
+          u.w = pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+  (void)D3;
+}
+
+}  // namespace
+
+int attention_tc(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, int num_sms, cudaStream_t s) {
+  SWC_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, "attention_tc: buffers must be 16-byte aligned");
+  CUtensorMap tm;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)(3 * H * HD), (cuuint64_t)nb * T};
+    cuuint64_t strides[1] = {(cuuint64_t)(3 * H * HD) * 2};
+    cuuint32_t box[2] = {HD, 128};
+    SWC_TRY(make_tmap(&tm, 1, qkv, 2, dims, strides, box));
+  }
+  AttnParams p{};
+  p.lens = lens; p.out = out; p.T = T; p.H = H; p.nb = nb;
+  p.n_qp = ceil_div(T, 2 * QT);
+  p.n_items = p.n_qp * H * nb;
+  static bool configured = false;
+  if (!configured) {
+    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  const int grid = std::min(p.n_items, num_sms);
+  ProfScope ps(KC_ATTN, s);
+  attention_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(tm, p);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace swc

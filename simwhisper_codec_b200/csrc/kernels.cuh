@@ -45,6 +45,8 @@ int istft_ola(const float* frames, const float* win_sq /*[640]*/, int nb, int T,
 int attention_simt(const void* qkv, int type, void* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
 // bf16 tensor-core flash attention (mma.sync m16n8k16), same contract
 int attention_mma(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
+// bf16 flash attention on tcgen05 / TMEM / TMA (attention_tc.cu), same contract
+int attention_tc(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, int num_sms, cudaStream_t s);
 
 // misc
 int fill_f32(float* p, float v, long long n, cudaStream_t s);

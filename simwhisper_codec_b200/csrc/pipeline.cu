@@ -4,6 +4,7 @@
 #include "pipeline.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace swc {
 
@@ -55,7 +56,11 @@ int run_gemm(Ctx& c, const GemmDesc& d, int kind, int a_type, int out_type) {
 int run_attention(Ctx& c, const void* qkv, void* out, const long long* lens, int nb, int T) {
   if (c.dry) return 0;
   const int at = c.m->act_type();
-  if (at == 1 && !c.force_simt) return attention_mma((const bf16*)qkv, (bf16*)out, lens, nb, T, c.m->heads, c.s);
+  if (at == 1 && !c.force_simt) {
+    static const bool use_mma = [] { const char* e = getenv("SWC_ATTENTION"); return e && e[0] == 'm'; }();   // "mma": legacy path
+    if (use_mma) return attention_mma((const bf16*)qkv, (bf16*)out, lens, nb, T, c.m->heads, c.s);
+    return attention_tc((const bf16*)qkv, (bf16*)out, lens, nb, T, c.m->heads, c.m->num_sms, c.s);
+  }
   return attention_simt(qkv, at, out, lens, nb, T, c.m->heads, c.s);
 }
 

@@ -78,9 +78,12 @@ def _attn_ref(qkv, lens, H):
     return o * ok[..., None]
 
 
-@pytest.mark.parametrize("backend,dtype,tol", [(0, torch.float32, 2e-5), (1, torch.bfloat16, 2e-2), (2, torch.bfloat16, 2e-2)])
-@pytest.mark.parametrize("B,T,lens", [(2, 100, [100, 37]), (3, 257, [257, 1, 130]), (1, 1500, [1500]), (2, 375, [64, 375])])
+@pytest.mark.parametrize("backend,dtype,tol", [(0, torch.float32, 2e-5), (1, torch.bfloat16, 2e-2), (2, torch.bfloat16, 2e-2),
+                                                (3, torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("B,T,lens", [(2, 100, [100, 37]), (3, 257, [257, 1, 130]), (1, 1500, [1500]), (2, 375, [64, 375]),
+                                      (3, 1500, [1500, 129, 700])])
 def test_attention(backend, dtype, tol, B, T, lens):
+    """backend 3 = tcgen05/TMEM flash attention (the product path in bf16 mode), 2 = legacy mma.sync kernel."""
     lib = _lib.load()
     H = 12
     g = torch.Generator(device="cuda").manual_seed(T)
@@ -95,3 +98,25 @@ def test_attention(backend, dtype, tol, B, T, lens):
     diff = ((out.double() - ref) * ok[..., None]).abs().max().item()
     assert diff < tol, diff
     assert torch.isfinite(out).all()          # padded query rows are written (zeros), never left as garbage
+
+
+@pytest.mark.parametrize("backend", [2, 3])
+def test_attention_growing_maximum(backend):
+    """Scores whose row maximum keeps growing along the keys (ramp) force the online-softmax rescale path
+    (the tcgen05 kernel rescales lazily, only when the maximum grew by more than 2^8)."""
+    lib = _lib.load()
+    B, T, H = 2, 640, 12
+    g = torch.Generator(device="cuda").manual_seed(7)
+    qkv = torch.randn(B, T, 3 * H * 64, device="cuda", generator=g) * 0.5
+    ramp = torch.linspace(0.0, 6.0, T, device="cuda")
+    qkv[..., H * 64: 2 * H * 64] += ramp[None, :, None] * 0.3          # keys drift along time
+    qkv[..., : H * 64] = qkv[..., : H * 64].abs() * 0.4                # positive queries -> scores grow with the key index
+    qkv = qkv.bfloat16()
+    lens_t = torch.tensor([T, 333], device="cuda", dtype=torch.int64)
+    out = torch.full((B, T, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.swc_test_attention(backend, _p(qkv), _p(out), _p(lens_t), B, T, H, _stream()), "attention")
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv, lens_t, H)
+    ok = torch.arange(T, device="cuda")[None, :] < lens_t[:, None]
+    diff = ((out.double() - ref) * ok[..., None]).abs().max().item()
+    assert diff < 2e-2, diff
