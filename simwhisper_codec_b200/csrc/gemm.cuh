@@ -94,6 +94,31 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
+// two GELUs per instruction on the packed-fp32 pipe (fma.rn.f32x2 / mul.rn.f32x2, sm_100): same polynomial as
+// gelu_fast, so results are bit-identical to it.
+__device__ __forceinline__ void gelu_fast2(float& a, float& b) {
+  const float x2a = fminf(a * a, 36.0f), x2b = fminf(b * b, 36.0f);
+  unsigned long long x, x2, poly, c0, c1, c2, half;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "f"(x2a), "f"(x2b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(-0.000351517274f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c1) : "f"(0.0370056493f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c0) : "f"(0.79750788f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(half) : "f"(0.5f));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(poly) : "l"(c2), "l"(x2), "l"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(poly) : "l"(poly), "l"(x2), "l"(c0));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(poly) : "l"(x), "l"(poly));
+  float ta, tb;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(ta), "=f"(tb) : "l"(poly));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(ta));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(tb));
+  unsigned long long t, hx, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(ta), "f"(tb));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(hx) : "l"(x), "l"(half));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(hx), "l"(t), "l"(hx));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
+}
+
 template <int KIND, typename TO>
 __device__ __forceinline__ void epi_apply(const EpiParams& p, int b, int m, int n0, int N, int m_rows,
                                           float (&v)[8], const float* bias8, const float* gamma8) {
@@ -201,7 +226,19 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int b, int m, int 
       r[2 * j] = mag * c;
       r[2 * j + 1] = mag * s;
     }
-    store8(o, r);   // the S buffer is padded to a multiple of 8 columns; pad columns meet zero iDFT rows
+    if (p.out2) {   // tensor-core iDFT: S = s1 + s2 as two bf16 planes [row][s1 (N) | s2 (N)] in the same bytes as the fp32 row
+      bf16* o2 = p.out2 + 2 * ((long long)b * p.out_batch_stride + (long long)m * p.out_row_stride) + n0;
+      float hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        hi[j] = __bfloat162float(__float2bfloat16_rn(r[j]));
+        lo[j] = r[j] - hi[j];
+      }
+      store8(o2, hi);
+      store8(o2 + N, lo);
+    } else {
+      store8(o, r);   // the S buffer is padded to whole K slabs; pad columns meet zero iDFT rows
+    }
   }
 }
 

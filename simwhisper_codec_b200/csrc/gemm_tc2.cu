@@ -11,7 +11,7 @@
 //   warp 0    : TMA producer (both CTAs; with CG = 2 all completions land on the leader's `full` barrier)
 //   warp 1    : MMA issuer (leader CTA only); tcgen05.commit multicasts `empty`/`tfull` to both CTAs
 //   warp 2    : TMEM allocator
-//   warps 4-11: epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / GELU / gamma in registers -> 128B-swizzled
+//   warps 4-11: epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / GELU / gamma (packed f32x2) -> 128B-swizzled
 //               shared staging (one 32-row x 128-byte box per warp) -> cp.async.bulk.tensor store.  Stores are
 //               whole 128-byte lines and TMA clips rows >= m_rows and columns >= N.
 // Persistent: grid = CG * min(#tiles, #SMs / CG); tiles are walked n-fastest so the clusters resident at any
@@ -71,8 +71,7 @@ struct Smem2 {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutOff = STAGES * kStageBytes;
   static constexpr int kOutBytesPerWarp = 32 * 128;                     // 32 rows x 128-byte swizzle line
-  static constexpr int kVecOff = kOutOff + kEpiWarps * NBUF * kOutBytesPerWarp;
-  static constexpr int kBarOff = kVecOff + 4 * BN * 4;                  // bias[2][BN], gamma[2][BN]
+  static constexpr int kBarOff = kOutOff + kEpiWarps * NBUF * kOutBytesPerWarp;
   static constexpr int kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
   static_assert(kTotal <= 232448, "shared memory budget");
 };
@@ -92,7 +91,34 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int CG, int STAGES, int NBUF, int ACT, typename TO>
+__device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+// 4 accumulator columns -> (act(acc + bias)) * gamma.  bias / gamma are read straight from global memory: the
+// address is uniform across the warp (one L1 transaction per load) and the vectors stay L1-resident.
+template <int ACT, bool GAMMA>
+__device__ __forceinline__ void epi4(const uint32_t* acc, const float* sb, const float* sg, bool in_range, float* v) {
+  const float4 b4 = (sb && in_range) ? __ldg(reinterpret_cast<const float4*>(sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned long long lo, hi;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(lo) : "l"(pack_f32x2(__uint_as_float(acc[0]), __uint_as_float(acc[1]))), "l"(pack_f32x2(b4.x, b4.y)));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(hi) : "l"(pack_f32x2(__uint_as_float(acc[2]), __uint_as_float(acc[3]))), "l"(pack_f32x2(b4.z, b4.w)));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v[0]), "=f"(v[1]) : "l"(lo));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v[2]), "=f"(v[3]) : "l"(hi));
+  if constexpr (ACT == 2) {
+    gelu_fast2(v[0], v[1]);
+    gelu_fast2(v[2], v[3]);
+  } else if constexpr (ACT == 1) {
+    v[0] = gelu_erf(v[0]); v[1] = gelu_erf(v[1]); v[2] = gelu_erf(v[2]); v[3] = gelu_erf(v[3]);
+  }
+  if constexpr (GAMMA) {
+    const float4 g4 = in_range ? __ldg(reinterpret_cast<const float4*>(sg)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    v[0] *= g4.x; v[1] *= g4.y; v[2] *= g4.z; v[3] *= g4.w;
+  }
+}
+
+template <int CG, int STAGES, int NBUF, int ACT, bool GAMMA, typename TO>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmO, const Tc2Params p) {
@@ -104,7 +130,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tfull = empty + STAGES;     // [2] accumulator ready (per CTA)
   uint64_t* tempty = tfull + 2;         // [2] accumulator drained (leader CTA collects both CTAs' epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* svec = reinterpret_cast<float*>(smem + L::kVecOff);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
@@ -189,8 +214,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int ew = warp - 4;
     const int lg = ew & 3;                    // TMEM lane group of this warp: lanes [32 lg, 32 lg + 32)
     const int c_base = (ew >> 2) * (BN / 2);  // this warp's 128 accumulator columns
-    const int etid = threadIdx.x - 128;
-    constexpr int kEpiThreads = 32 * kEpiWarps;
     constexpr bool kF32 = sizeof(TO) == 4;
     uint8_t* stage_out = smem + L::kOutOff + ew * NBUF * L::kOutBytesPerWarp;
     const uint32_t tempty_leader[2] = {CG == 1 ? smem_u32(&tempty[0]) : mapa(smem_u32(&tempty[0]), 0),
@@ -203,15 +226,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int r = tile - b * tiles_per_batch;
       const int m0 = (r / p.n_tiles) * (BM * CG) + (int)rank * BM;
       const int n0 = (r % p.n_tiles) * BN;
-      // stage this tile's per-column vectors (overlaps the MMAs of this tile)
-      float* sb = svec + acc * BN;
-      float* sg = svec + (2 + acc) * BN;
-      for (int i = etid; i < BN; i += kEpiThreads) {
-        const int n = n0 + i;
-        sb[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
-        sg[i] = (p.gamma && n < p.N) ? __ldg(p.gamma + n) : 1.0f;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + c_base;
@@ -232,33 +246,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
         }
         const uint32_t box = smem_u32(stage_out + obuf * L::kOutBytesPerWarp) + (uint32_t)lane * 128u;
-        const float* sbc = sb + c_base + sub * 32;
-        const float* sgc = sg + c_base + sub * 32;
+        const int ncol = n0 + c_base + sub * 32;      // first of this sub-chunk's 32 columns
+        const float* sbc = p.bias ? p.bias + ncol : nullptr;
+        const float* sgc = GAMMA ? p.gamma + ncol : nullptr;
         if constexpr (kF32) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sbc + 4 * q);
-            const float4 g4 = *reinterpret_cast<const float4*>(sgc + 4 * q);
-            const float v0 = act_apply<ACT>(__uint_as_float(rr[sub & 1][4 * q + 0]) + b4.x) * g4.x;
-            const float v1 = act_apply<ACT>(__uint_as_float(rr[sub & 1][4 * q + 1]) + b4.y) * g4.y;
-            const float v2 = act_apply<ACT>(__uint_as_float(rr[sub & 1][4 * q + 2]) + b4.z) * g4.z;
-            const float v3 = act_apply<ACT>(__uint_as_float(rr[sub & 1][4 * q + 3]) + b4.w) * g4.w;
-            st_shared_v4(box + (((uint32_t)q ^ sw) << 4), __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2),
-                         __float_as_uint(v3));
+            float v[4];
+            epi4<ACT, GAMMA>(&rr[sub & 1][4 * q], sbc ? sbc + 4 * q : nullptr, sgc + 4 * q, ncol + 4 * q + 4 <= p.N, v);
+            st_shared_v4(box + (((uint32_t)q ^ sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                         __float_as_uint(v[3]));
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float v[8];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float4 b4 = *reinterpret_cast<const float4*>(sbc + 8 * q + 4 * h);
-              const float4 g4 = *reinterpret_cast<const float4*>(sgc + 8 * q + 4 * h);
-              v[4 * h + 0] = act_apply<ACT>(__uint_as_float(rr[sub & 1][8 * q + 4 * h + 0]) + b4.x) * g4.x;
-              v[4 * h + 1] = act_apply<ACT>(__uint_as_float(rr[sub & 1][8 * q + 4 * h + 1]) + b4.y) * g4.y;
-              v[4 * h + 2] = act_apply<ACT>(__uint_as_float(rr[sub & 1][8 * q + 4 * h + 2]) + b4.z) * g4.z;
-              v[4 * h + 3] = act_apply<ACT>(__uint_as_float(rr[sub & 1][8 * q + 4 * h + 3]) + b4.w) * g4.w;
-            }
+            epi4<ACT, GAMMA>(&rr[sub & 1][8 * q], sbc ? sbc + 8 * q : nullptr, sgc + 8 * q, ncol + 8 * q + 4 <= p.N, v);
+            epi4<ACT, GAMMA>(&rr[sub & 1][8 * q + 4], sbc ? sbc + 8 * q + 4 : nullptr, sgc + 8 * q + 4, ncol + 8 * q + 8 <= p.N, v + 4);
             const uint32_t chunk = (uint32_t)((sub & 1) * 4 + q);
             st_shared_v4(box + ((chunk ^ sw) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
                          pack_bf16(v[6], v[7]));
@@ -291,7 +295,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int CG, int STAGES, int NBUF, int ACT, typename TO>
+template <int CG, int STAGES, int NBUF, int ACT, bool GAMMA, typename TO>
 int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
   using L = Smem2<CG, STAGES, NBUF>;
   constexpr int out_type = sizeof(TO) == 4 ? 0 : 1;
@@ -325,7 +329,7 @@ int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
   p.n_taps = d.n_taps; p.kb_per_tap = d.tap_k / BK;
   for (int i = 0; i < d.n_taps; ++i) { p.tap_row[i] = d.tap_row[i]; p.tap_col[i] = d.tap_col[i]; }
   p.bias = d.epi.bias; p.gamma = d.epi.gamma;
-  auto kern = gemm_tc2_kernel<CG, STAGES, NBUF, ACT, TO>;
+  auto kern = gemm_tc2_kernel<CG, STAGES, NBUF, ACT, GAMMA, TO>;
   static bool configured = false;
   if (!configured) {
     SWC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -350,14 +354,16 @@ int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
 template <int CG, int STAGES, int NBUF>
 int dispatch2(const GemmDesc& d, int out_type, int num_sms, cudaStream_t s) {
   const int act = d.epi.act;
+  const bool gamma = d.epi.gamma != nullptr;
   if (out_type == 0) {
-    if (act == 0) return launch2<CG, STAGES, NBUF, 0, float>(d, num_sms, s);
-    if (act == 2) return launch2<CG, STAGES, NBUF, 2, float>(d, num_sms, s);
+    if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, 0, false, float>(d, num_sms, s);
+    if (act == 0 && gamma) return launch2<CG, STAGES, NBUF, 0, true, float>(d, num_sms, s);
+    if (act == 2 && !gamma) return launch2<CG, STAGES, NBUF, 2, false, float>(d, num_sms, s);
   } else {
-    if (act == 0) return launch2<CG, STAGES, NBUF, 0, bf16>(d, num_sms, s);
-    if (act == 2) return launch2<CG, STAGES, NBUF, 2, bf16>(d, num_sms, s);
+    if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, 0, false, bf16>(d, num_sms, s);
+    if (act == 2 && !gamma) return launch2<CG, STAGES, NBUF, 2, false, bf16>(d, num_sms, s);
   }
-  set_error("gemm_tc2: unsupported activation %d", act);
+  set_error("gemm_tc2: unsupported epilogue (act %d, gamma %d, out type %d)", act, (int)gamma, out_type);
   return -1;
 }
 
@@ -366,6 +372,7 @@ int dispatch2(const GemmDesc& d, int out_type, int num_sms, cudaStream_t s) {
 // which EPI_STORE problems the second-generation kernel takes
 bool gemm_tc2_eligible(const GemmDesc& d) {
   const EpiParams& e = d.epi;
+  if (e.gamma && e.act != 0) return false;       // gamma only accompanies the plain fp32 pwconv2 epilogue
   return e.residual == nullptr && e.out2 == nullptr && (e.act == 0 || e.act == 2) && d.N >= 256 && d.N % 8 == 0 &&
          d.tap_k % BK == 0 && ((uintptr_t)e.out & 15) == 0;
 }
@@ -375,8 +382,9 @@ int gemm_tc2(const GemmDesc& d, int out_type, int num_sms, int variant, cudaStre
   SWC_REQUIRE(gemm_tc2_eligible(d), "gemm_tc2: problem not eligible (residual/out2/act/N)");
   SWC_REQUIRE(d.m_rows > 0 && d.nb > 0, "gemm_tc2: empty problem");
   SWC_REQUIRE(((uintptr_t)d.A & 15) == 0 && ((uintptr_t)d.W & 15) == 0, "gemm_tc2: operands must be 16-byte aligned");
-  if (variant == 1) return dispatch2<1, 3, 2>(d, out_type, num_sms, s);
-  return dispatch2<2, 4, 2>(d, out_type, num_sms, s);
+  if (variant == 1) return dispatch2<1, 4, 1>(d, out_type, num_sms, s);
+  if (variant == 3) return dispatch2<2, 5, 2>(d, out_type, num_sms, s);   // one stage fewer, double-buffered staging boxes
+  return dispatch2<2, 6, 1>(d, out_type, num_sms, s);                     // deepest operand ring that fits 227 KB
 }
 
 }  // namespace swc

@@ -18,6 +18,17 @@ namespace {
 
 const double kPi = 3.14159265358979323846;
 
+// round-to-nearest-even to bf16 precision, kept as float (exactly representable, so the bf16 upload is lossless)
+static float bf16_round(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return f;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  u &= 0xffff0000u;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
 struct Packer {
   Model& m;
   std::string err;
@@ -267,8 +278,8 @@ int pack_model(Model& m) {
     }
     P.copy_vec("voc.final.g", "vocos.backbone.final_layer_norm.weight", V);
     P.copy_vec("voc.final.b", "vocos.backbone.final_layer_norm.bias", V);
-    // head: interleave (log-magnitude_j, phase_j) rows; pad 642 -> 656 zero rows
-    const int NB = m.n_fft / 2 + 1, NO = 2 * NB, NP = (NO + 15) / 16 * 16;
+    // head: interleave (log-magnitude_j, phase_j) rows; pad 642 -> 704 zero rows (their spectrum is (1, 0): finite, and it meets zero iDFT columns)
+    const int NB = m.n_fft / 2 + 1, NO = 2 * NB, NP = (NO + 63) / 64 * 64;   // 642 -> 704: whole 64-wide K slabs for the iDFT GEMM
     if (const RawTensor* w = P.raw("vocos.head.out.weight", {NO, V})) {
       const RawTensor* b = P.raw("vocos.head.out.bias", {NO});
       auto& o = P.put("voc.head.w", (size_t)NP * V, true);
@@ -295,6 +306,17 @@ int pack_model(Model& m) {
         }
         w2[n] = win->f[n] * win->f[n];
       }
+      // bf16 tensor-core form of the same operand: w = w1 + w2 (+ 2^-17 relative), rows [w1 | w2 | w1] so that one GEMM
+      // over the taps (s1, s1, s2) of a split spectrum s = s1 + s2 accumulates s1 w1 + s1 w2 + s2 w1 in fp32
+      auto& o3 = P.put("voc.idft.w3", (size_t)N * 3 * NP, true);
+      for (int n = 0; n < N; ++n)
+        for (int k = 0; k < NP; ++k) {
+          const float w = o[(size_t)n * NP + k];
+          const float w1 = bf16_round(w), w2r = bf16_round(w - w1);
+          o3[(size_t)n * 3 * NP + k] = w1;
+          o3[(size_t)n * 3 * NP + NP + k] = w2r;
+          o3[(size_t)n * 3 * NP + 2 * NP + k] = w1;
+        }
     }
   }
   // ---- log-mel tables (reference feature_extractor.py:50-58, 92-101)
@@ -437,9 +459,10 @@ int upload_model(Model& m, int device) {
     b.pw1 = L(p + ".pw1", I, I, V);
     b.pw2 = L(p + ".pw2", V, V, I);
   }
-  const int NP = ((m.n_fft + 2) + 15) / 16 * 16;
+  const int NP = ((m.n_fft + 2) + 63) / 64 * 64;
   m.voc_head = L("voc.head", NP, NP, V);
   m.w_idft = F("voc.idft.w"); m.win_sq = F("voc.win_sq");
+  m.w_idft3 = m.tab.count("voc.idft.w3") ? m.tab["voc.idft.w3"].dev : nullptr;
   m.w_dft = F("mel.dft.w"); m.w_melfb = F("mel.fb.w");
   m.uploaded = true;
   (void)g_slab_unused;

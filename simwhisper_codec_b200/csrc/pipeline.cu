@@ -333,12 +333,24 @@ int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav) {
     SWC_TRY(layernorm(x, pending ? delta : nullptr, nullptr, y, at, m.voc_final_g, m.voc_final_b, 1e-6f, nb, Tv, Tv, V, nullptr, c.s));
     float* S = (float*)region;
     float* frames = S + rows * NP;
-    {   // head GEMM with exp/clip/sincos epilogue -> interleaved complex spectrum (fp32)
+    const bool tc_idft = at == 1 && !c.force_simt && m.w_idft3 != nullptr;
+    {   // head GEMM with exp/clip/sincos epilogue -> interleaved complex spectrum (fp32, or split bf16 planes s1|s2)
       GemmDesc d = base_desc(y, V, 0, (int)rows, V, (int)rows, 1, m.voc_head);
       set_out(d, S, NP, 0);
+      if (tc_idft) d.epi.out2 = (bf16*)S;
       SWC_TRY(run_gemm(c, d, EPI_HEAD, at, 0));
     }
-    {   // windowed inverse real DFT as an fp32 GEMM
+    if (tc_idft) {
+      // windowed inverse real DFT on the tensor cores with fp32-class accuracy: three bf16 products
+      // s1 w1 + s1 w2 + s2 w1 accumulated in fp32 (taps select the s plane, the packed operand holds w1|w2|w1)
+      LinearW wi; wi.w = m.w_idft3; wi.bias = nullptr; wi.N = m.n_fft; wi.w_rows = m.n_fft; wi.K = NP;
+      GemmDesc d = base_desc(S, 2 * NP, 0, (int)rows, 2 * NP, (int)rows, 1, wi);
+      d.n_taps = 3; d.tap_k = NP;
+      d.tap_row[0] = d.tap_row[1] = d.tap_row[2] = 0;
+      d.tap_col[0] = 0; d.tap_col[1] = 0; d.tap_col[2] = NP;
+      set_out(d, frames, m.n_fft, 0);
+      SWC_TRY(run_gemm(c, d, EPI_STORE, 1, 0));
+    } else {   // fp32 parity mode: the same contraction as an fp32 FFMA GEMM
       LinearW wi; wi.w = m.w_idft; wi.bias = nullptr; wi.N = m.n_fft; wi.w_rows = m.n_fft; wi.K = NP;
       GemmDesc d = base_desc(S, NP, 0, (int)rows, NP, (int)rows, 1, wi);
       set_out(d, frames, m.n_fft, 0);

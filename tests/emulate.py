@@ -155,11 +155,11 @@ class Emu:
             g = F.gelu(y @ self.t(p + ".pw1.w", I, V).T + self.t(p + ".pw1.b"))
             x = x + (g @ self.t(p + ".pw2.w", V, I).T + self.t(p + ".pw2.b")) * self.t(p + ".gamma")
         y = self.ln(x, "voc.final.g", "voc.final.b", 1e-6)
-        hd = y @ self.t("voc.head.w", 656, V).T + self.t("voc.head.b")
+        hd = y @ self.t("voc.head.w", 704, V).T + self.t("voc.head.b")
         mag = torch.exp(hd[..., 0::2]).clamp(max=100.0)
         ph = hd[..., 1::2]
-        S = torch.stack([mag * torch.cos(ph), mag * torch.sin(ph)], dim=-1).reshape(nb, Tv, 656)
-        frames = S @ self.t("voc.idft.w", 640, 656).T
+        S = torch.stack([mag * torch.cos(ph), mag * torch.sin(ph)], dim=-1).reshape(nb, Tv, 704)
+        frames = S @ self.t("voc.idft.w", 640, 704).T
         w2 = self.t("voc.win_sq")
         L = 160 * Tv
         out = torch.zeros(nb, L, dtype=self.dt)
