@@ -1,12 +1,14 @@
 // bf16 flash attention on tcgen05 (reference audiocodec/nn/modules.py:145-187): non-causal, head_dim 64, keys >=
 // lens[b] masked, q pre-scaled by the packed q_proj.  Persistent, warp-specialised, two 128-query tiles per work item:
 //
-//   warp 0      TMA producer: Q tiles (once per item) and a 3-stage ring of K|V tiles (128 keys x 64 x bf16 each)
-//   warp 1      MMA issuer (one lane) + TMEM allocator
+//   warp 0      TMA producer: Q tiles (double-buffered per item) and a 4-stage ring of K|V tiles (128 keys x 64 x bf16 each)
+//   warp 1, 2   MMA issuer of query tile 0 / 1 (one lane each; warp 1 also owns the TMEM allocation)
 //                 S_i = Q_i K_j^T   UMMA M128 N128 K16 x4, both operands K-major from shared memory -> TMEM (fp32)
 //                 O_i += P_i V_j    UMMA M128 N64  K16 x8, A = P_i (bf16) from TMEM, B = V_j MN-major from shared memory
-//   warps 2-5   softmax warpgroup of query tile 0 (one thread = one query row = one TMEM lane)
-//   warps 6-9   softmax warpgroup of query tile 1
+//               one issuer per tile: each blocks only on its own tile's barriers (a single issuer either serialises the
+//               two warpgroups or pays ~150 cycles per polled barrier), and S runs one key block ahead of P V.
+//   warps 3-6   softmax warpgroup of query tile 0 (one thread = one query row = one TMEM lane)
+//   warps 7-10  softmax warpgroup of query tile 1
 //
 // The two tiles ping-pong: while one warpgroup exponentiates S_i(j) the tensor core computes S_{1-i} / P V of the other.
 // Per tile and key block a softmax thread reads its 128 scores from TMEM, takes the row maximum, and only when the
@@ -24,12 +26,12 @@ namespace {
 
 using namespace ptx;
 
-constexpr int QT = 128, KT = 128, HD = 64, STAGES = 3;
-constexpr int kThreads = 320;
+constexpr int QT = 128, KT = 128, HD = 64, STAGES = 4;
+constexpr int kThreads = 352;
 constexpr int kTileBytes = 128 * 64 * 2;                 // 16 KB: Q, K or V tile
-constexpr int kQOff = 0, kKVOff = 2 * kTileBytes;
+constexpr int kQOff = 0, kKVOff = 4 * kTileBytes;      // Q: [tile][buffer]
 constexpr int kBarOff = kKVOff + STAGES * 2 * kTileBytes;
-constexpr int kNumBars = 2 + 2 + 2 * STAGES + 2 + 2 + 2 + 2 + 2;
+constexpr int kNumBars = 4 + 4 + 2 * STAGES + 2 + 2 + 2 + 2 + 2;
 constexpr int kSmemBytes = kBarOff + kNumBars * 8 + 16 + 1024;
 constexpr uint32_t kColS = 0, kColP = 256, kColO = 384;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -75,9 +77,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
-  uint64_t* q_full = bars;               // [2]
-  uint64_t* q_empty = q_full + 2;        // [2]
-  uint64_t* kv_full = q_empty + 2;       // [STAGES]
+  uint64_t* q_full = bars;               // [tile][buffer]
+  uint64_t* q_empty = q_full + 4;        // [tile][buffer]
+  uint64_t* kv_full = q_empty + 4;       // [STAGES]
   uint64_t* kv_empty = kv_full + STAGES; // [STAGES]
   uint64_t* s_full = kv_empty + STAGES;  // [2] S_i written by the tensor core
   uint64_t* s_free = s_full + 2;         // [2] S_i copied to registers by its warpgroup (4 warps)
@@ -90,12 +92,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQKV);
+    for (int i = 0; i < 4; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
       mbar_init(&p_full[i], 4); mbar_init(&o_done[i], 1); mbar_init(&o_free[i], 4);
     }
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }   // both tiles' issuers release a slot
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
@@ -115,9 +117,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         if (it.dead) continue;
         const int row0 = it.b * p.T;
         for (int i = 0; i < it.n_act; ++i) {
-          mbar_wait(&q_empty[i], (q_cnt[i] & 1) ^ 1);
-          mbar_expect_tx(&q_full[i], kTileBytes);
-          tma_load_2d<1>(&tmQKV, smem_u32(&q_full[i]), smem + kQOff + i * kTileBytes, it.h * HD, row0 + it.q0 + i * QT);
+          const uint32_t qb = i * 2 + (q_cnt[i] & 1);
+          mbar_wait(&q_empty[qb], ((q_cnt[i] >> 1) & 1) ^ 1);
+          mbar_expect_tx(&q_full[qb], kTileBytes);
+          tma_load_2d<1>(&tmQKV, smem_u32(&q_full[qb]), smem + kQOff + qb * kTileBytes, it.h * HD, row0 + it.q0 + i * QT);
           ++q_cnt[i];
         }
         for (int j = 0; j < it.n_kt; ++j, ++kv_it) {
@@ -130,63 +133,89 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp <= 2) {
+    // ------------------------------------------------------------------ MMA issuer of query tile i
     if (lane == 0) {
+      const int i = warp - 1;
       constexpr uint32_t idesc_s = make_idesc(QT, KT);          // Q K^T: both K-major
       constexpr uint32_t idesc_o = make_idesc(QT, HD, 1);       // P V: B = V is MN-major ([key][dim], dim contiguous)
-      uint32_t q_cnt[2] = {0, 0}, s_cnt[2] = {0, 0}, pv_cnt[2] = {0, 0}, item_cnt[2] = {0, 0};
-      uint32_t kv_it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const Item it = decode_item(p, item);
-        if (it.dead) continue;
-        auto issue_s = [&](int i, uint32_t st, bool last) {
-          mbar_wait(&s_free[i], (s_cnt[i] & 1) ^ 1);            // the previous S_i has been copied out
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(smem + kQOff + i * kTileBytes));
-          const uint64_t bdesc = make_smem_desc(smem_u32(smem + kKVOff + st * 2 * kTileBytes));
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_bf16<1>(tmem_base + kColS + i * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-          umma_commit<1>(&s_full[i]);
-          if (last) umma_commit<1>(&q_empty[i]);
-          ++s_cnt[i];
-        };
-        for (int i = 0; i < it.n_act; ++i) { mbar_wait(&q_full[i], q_cnt[i] & 1); ++q_cnt[i]; }
-        {
-          const uint32_t st = kv_it % STAGES, ph = (kv_it / STAGES) & 1;
-          mbar_wait(&kv_full[st], ph);
-          tc_fence_after();
-          for (int i = 0; i < it.n_act; ++i) issue_s(i, st, it.n_kt == 1);
+      // cursor over the (item, key block) pairs of this CTA, in the producer's ring order
+      struct Cursor {
+        int item, j, n_kt;
+        bool active;          // tile i takes part in `item`
+        uint32_t g;           // ring index of (item, j)
+        uint32_t n_items;     // items with tile i active that lie behind the cursor
+      };
+      auto load_item = [&](Cursor& c) {            // position on the first non-dead item >= c.item
+        for (; c.item < p.n_items; c.item += gridDim.x) {
+          const Item it = decode_item(p, c.item);
+          if (it.dead) continue;
+          c.n_kt = it.n_kt; c.active = i < it.n_act; c.j = 0;
+          return;
         }
-        for (int j = 0; j < it.n_kt; ++j, ++kv_it) {
-          const uint32_t st = kv_it % STAGES;
-          for (int i = 0; i < it.n_act; ++i) {
-            if (j + 1 < it.n_kt) {
-              const uint32_t st1 = (kv_it + 1) % STAGES, ph1 = ((kv_it + 1) / STAGES) & 1;
-              if (i == 0) { mbar_wait(&kv_full[st1], ph1); tc_fence_after(); }
-              issue_s(i, st1, j + 2 == it.n_kt);
-            }
-            mbar_wait(&p_full[i], pv_cnt[i] & 1);
-            if (j == 0) mbar_wait(&o_free[i], (item_cnt[i] & 1) ^ 1);   // the previous item's O_i has been read
-            tc_fence_after();
-            const uint32_t vaddr = smem_u32(smem + kKVOff + st * 2 * kTileBytes + kTileBytes);
-#pragma unroll
-            for (int k = 0; k < KT / 16; ++k) {
-              // A: 16 keys = 8 packed columns of P_i; B: 16 key rows of V = 2 swizzle atoms of 8 rows x 128 B
-              umma_bf16_ts(tmem_base + kColO + i * 64, tmem_base + kColP + i * 64 + k * 8, make_smem_desc(vaddr + k * 2048), idesc_o,
-                           (j | k) != 0);
-            }
-            umma_commit<1>(&o_done[i]);
-            ++pv_cnt[i];
-          }
-          umma_commit<1>(&kv_empty[st]);
+      };
+      auto advance = [&](Cursor& c) {
+        ++c.g;
+        if (++c.j == c.n_kt) {
+          if (c.active) ++c.n_items;
+          c.item += gridDim.x;
+          load_item(c);
         }
-        for (int i = 0; i < it.n_act; ++i) ++item_cnt[i];
+      };
+      Cursor cs{blockIdx.x, 0, 0, false, 0, 0}, cp{blockIdx.x, 0, 0, false, 0, 0};
+      load_item(cs);
+      load_item(cp);
+      uint32_t n_s = 0, n_p = 0;
+      auto skip_inactive = [&](Cursor& c) {        // the S cursor only visits items in which this tile is active
+        while (c.item < p.n_items && !c.active) { c.g += c.n_kt; c.item += gridDim.x; load_item(c); }
+      };
+      auto issue_s = [&]() {
+        const uint32_t slot = cs.g % STAGES, qb = i * 2 + (cs.n_items & 1);
+        if (cs.j == 0) mbar_wait(&q_full[qb], (cs.n_items >> 1) & 1);
+        mbar_wait(&kv_full[slot], (cs.g / STAGES) & 1);
+        mbar_wait(&s_free[i], (n_s & 1) ^ 1);                   // the previous S_i has been copied out by the warpgroup
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_u32(smem + kQOff + qb * kTileBytes));
+        const uint64_t bdesc = make_smem_desc(smem_u32(smem + kKVOff + slot * 2 * kTileBytes));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16<1>(tmem_base + kColS + i * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+        umma_commit<1>(&s_full[i]);
+        ++n_s;
+        if (cs.j + 1 == cs.n_kt) umma_commit<1>(&q_empty[qb]);  // last use of this Q buffer
+        advance(cs);
+        skip_inactive(cs);
+      };
+      skip_inactive(cs);
+      if (cs.item < p.n_items) issue_s();                        // S runs one key block ahead of P V
+      while (cp.item < p.n_items) {
+        const uint32_t slot = cp.g % STAGES;
+        if (!cp.active) {
+          // this tile sits the item out but still owes the ring its release: in ring order, once the slot has landed
+          mbar_wait(&kv_full[slot], (cp.g / STAGES) & 1);
+          mbar_arrive(&kv_empty[slot]);
+          advance(cp);
+          continue;
+        }
+        if (cs.item < p.n_items) issue_s();
+        mbar_wait(&p_full[i], n_p & 1);
+        if (cp.j == 0) mbar_wait(&o_free[i], (cp.n_items & 1) ^ 1);   // the previous item's O_i has been read out
+        tc_fence_after();
+        const uint32_t vaddr = smem_u32(smem + kKVOff + slot * 2 * kTileBytes + kTileBytes);
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k) {
+          // A: 16 keys = 8 packed columns of P_i; B: 16 key rows of V = 2 swizzle atoms of 8 rows x 128 B
+          umma_bf16_ts(tmem_base + kColO + i * 64, tmem_base + kColP + i * 64 + k * 8, make_smem_desc(vaddr + k * 2048), idesc_o,
+                       (cp.j | k) != 0);
+        }
+        umma_commit<1>(&o_done[i]);
+        umma_commit<1>(&kv_empty[slot]);
+        ++n_p;
+        advance(cp);
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
-    const int i = (warp - 2) >> 2;                    // query tile of this warpgroup
+    const int i = (warp - 3) >> 2;                    // query tile of this warpgroup
     const int lg = warp & 3;                          // TMEM lane group this warp may access
     const int row = lg * 32 + lane;                   // query row inside the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
