@@ -34,7 +34,8 @@ GF_TOTAL = 1311.86
 GF_ATTN = 24 * 6.912
 GF_MEL = 1.061
 GF_IDFT = 2.465
-GF_TC_GEMM = GF_TOTAL - GF_ATTN - GF_MEL - GF_IDFT       # contractions that run on the tcgen05 GEMM kernel
+GF_TC_GEMM = GF_TOTAL - GF_ATTN - GF_MEL              # contractions that run on the tcgen05 GEMM kernels (the inverse DFT
+                                                       # included: it runs as a 3-product split-bf16 GEMM, counted once)
 
 
 def gen_params():
@@ -117,7 +118,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="30 s windows per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--max-batch", type=int, default=int(os.environ.get("SWC_MAX_BATCH", 64)))
+    ap.add_argument("--max-batch", type=int, default=int(os.environ.get("SWC_MAX_BATCH", 128)),
+                    help="windows per kernel launch (the 256-window step runs as 256/max_batch sub-batches)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
