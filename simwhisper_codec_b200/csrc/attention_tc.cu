@@ -16,6 +16,7 @@
 // probabilities stay <= 256 and the final 1/l normalisation is exact); it then writes P as packed bf16 back to TMEM.
 // TMEM columns: S0 0-127 | S1 128-255 | P0 256-319 | P1 320-383 | O0 384-447 | O1 448-511.
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
@@ -27,12 +28,12 @@ namespace {
 using namespace ptx;
 
 constexpr int QT = 128, KT = 128, HD = 64, STAGES = 4;
-constexpr int kThreads = 352;
 constexpr int kTileBytes = 128 * 64 * 2;                 // 16 KB: Q, K or V tile
 constexpr int kQOff = 0, kKVOff = 4 * kTileBytes;      // Q: [tile][buffer]
 constexpr int kBarOff = kKVOff + STAGES * 2 * kTileBytes;
 constexpr int kNumBars = 4 + 4 + 2 * STAGES + 2 + 2 + 2 + 2 + 2;
-constexpr int kSmemBytes = kBarOff + kNumBars * 8 + 16 + 1024;
+constexpr int kXchOff = kBarOff + kNumBars * 8 + 16;     // float [tile][buffer][part][row] exchange slots (SPLIT = 2)
+constexpr int kSmemBytes = kXchOff + 2 * 2 * 2 * QT * 4 + 1024;
 constexpr uint32_t kColS = 0, kColP = 256, kColO = 384;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;                // log2 units
@@ -56,6 +57,7 @@ __device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
   it.q0 = qp * 2 * QT;
   long long l = p.lens ? p.lens[it.b] : p.T;
   it.len = (int)(l > p.T ? p.T : (l < 0 ? 0 : l));
+  it.len = (int)uniform_u32((uint32_t)it.len);      // same address in every lane: tell the compiler it is warp-uniform
   it.dead = it.q0 >= it.len;
   it.n_act = (it.q0 + QT < it.len) ? 2 : 1;
   it.n_kt = (it.len + KT - 1) / KT;
@@ -72,7 +74,24 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
+  static_assert(N == 32 || N == 64, "tmem_ld_n");
+#pragma unroll
+  for (int c = 0; c < N / 32; ++c) tmem_ld32(taddr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]) {
+  static_assert(N == 32 || N == 64, "tmem_st_n");
+#pragma unroll
+  for (int c = 0; c < N / 32; ++c) tmem_st32(taddr + c * 32, *reinterpret_cast<const uint32_t(*)[32]>(&r[c * 32]));
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__(96 + 256 * SPLIT, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -94,8 +113,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
     prefetch_tmap(&tmQKV);
     for (int i = 0; i < 4; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
-      mbar_init(&p_full[i], 4); mbar_init(&o_done[i], 1); mbar_init(&o_free[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4 * SPLIT);
+      mbar_init(&p_full[i], 4 * SPLIT); mbar_init(&o_done[i], 1); mbar_init(&o_free[i], 4 * SPLIT);
     }
     for (int i = 0; i < STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }   // both tiles' issuers release a slot
     fence_barrier_init();
@@ -104,12 +123,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   const int D3 = 3 * p.H * HD;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (whole warp in uniform control flow; one elected lane issues: see tc_ptx.cuh::elect_one)
+    {
       uint32_t q_cnt[2] = {0, 0};
       uint32_t kv_it = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -119,23 +139,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         for (int i = 0; i < it.n_act; ++i) {
           const uint32_t qb = i * 2 + (q_cnt[i] & 1);
           mbar_wait(&q_empty[qb], ((q_cnt[i] >> 1) & 1) ^ 1);
-          mbar_expect_tx(&q_full[qb], kTileBytes);
-          tma_load_2d<1>(&tmQKV, smem_u32(&q_full[qb]), smem + kQOff + qb * kTileBytes, it.h * HD, row0 + it.q0 + i * QT);
+          if (elect_one()) {
+            mbar_expect_tx(&q_full[qb], kTileBytes);
+            tma_load_2d<1>(&tmQKV, smem_u32(&q_full[qb]), smem + kQOff + qb * kTileBytes, it.h * HD, row0 + it.q0 + i * QT);
+          }
+          __syncwarp();
           ++q_cnt[i];
         }
         for (int j = 0; j < it.n_kt; ++j, ++kv_it) {
           const uint32_t st = kv_it % STAGES, ph = (kv_it / STAGES) & 1;
           mbar_wait(&kv_empty[st], ph ^ 1);
-          mbar_expect_tx(&kv_full[st], 2 * kTileBytes);
-          uint8_t* dst = smem + kKVOff + st * 2 * kTileBytes;
-          tma_load_2d<1>(&tmQKV, smem_u32(&kv_full[st]), dst, (p.H + it.h) * HD, row0 + j * KT);
-          tma_load_2d<1>(&tmQKV, smem_u32(&kv_full[st]), dst + kTileBytes, (2 * p.H + it.h) * HD, row0 + j * KT);
+          if (elect_one()) {
+            mbar_expect_tx(&kv_full[st], 2 * kTileBytes);
+            uint8_t* dst = smem + kKVOff + st * 2 * kTileBytes;
+            tma_load_2d<1>(&tmQKV, smem_u32(&kv_full[st]), dst, (p.H + it.h) * HD, row0 + j * KT);
+            tma_load_2d<1>(&tmQKV, smem_u32(&kv_full[st]), dst + kTileBytes, (2 * p.H + it.h) * HD, row0 + j * KT);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp <= 2) {
     // ------------------------------------------------------------------ MMA issuer of query tile i
-    if (lane == 0) {
+    {
       const int i = warp - 1;
       constexpr uint32_t idesc_s = make_idesc(QT, KT);          // Q K^T: both K-major
       constexpr uint32_t idesc_o = make_idesc(QT, HD, 1);       // P V: B = V is MN-major ([key][dim], dim contiguous)
@@ -177,11 +203,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         tc_fence_after();
         const uint64_t adesc = make_smem_desc(smem_u32(smem + kQOff + qb * kTileBytes));
         const uint64_t bdesc = make_smem_desc(smem_u32(smem + kKVOff + slot * 2 * kTileBytes));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16<1>(tmem_base + kColS + i * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-        umma_commit<1>(&s_full[i]);
+          for (int k = 0; k < HD / 16; ++k) umma_bf16<1>(tmem_base + kColS + i * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+          umma_commit<1>(&s_full[i]);
+          if (cs.j + 1 == cs.n_kt) umma_commit<1>(&q_empty[qb]);  // last use of this Q buffer
+        }
+        __syncwarp();
         ++n_s;
-        if (cs.j + 1 == cs.n_kt) umma_commit<1>(&q_empty[qb]);  // last use of this Q buffer
         advance(cs);
         skip_inactive(cs);
       };
@@ -192,7 +221,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         if (!cp.active) {
           // this tile sits the item out but still owes the ring its release: in ring order, once the slot has landed
           mbar_wait(&kv_full[slot], (cp.g / STAGES) & 1);
-          mbar_arrive(&kv_empty[slot]);
+          if (elect_one()) mbar_arrive(&kv_empty[slot]);
+          __syncwarp();
           advance(cp);
           continue;
         }
@@ -200,35 +230,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         mbar_wait(&p_full[i], n_p & 1);
         if (cp.j == 0) mbar_wait(&o_free[i], (cp.n_items & 1) ^ 1);   // the previous item's O_i has been read out
         tc_fence_after();
-        const uint32_t vaddr = smem_u32(smem + kKVOff + slot * 2 * kTileBytes + kTileBytes);
+        const uint64_t vdesc = make_smem_desc(smem_u32(smem + kKVOff + slot * 2 * kTileBytes + kTileBytes));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < KT / 16; ++k) {
-          // A: 16 keys = 8 packed columns of P_i; B: 16 key rows of V = 2 swizzle atoms of 8 rows x 128 B
-          umma_bf16_ts(tmem_base + kColO + i * 64, tmem_base + kColP + i * 64 + k * 8, make_smem_desc(vaddr + k * 2048), idesc_o,
-                       (cp.j | k) != 0);
+          for (int k = 0; k < KT / 16; ++k) {
+            // A: 16 keys = 8 packed columns of P_i; B: 16 key rows of V = 2 swizzle atoms of 8 rows x 128 B (+128 in >>4 units)
+            umma_bf16_ts(tmem_base + kColO + i * 64, tmem_base + kColP + i * 64 + k * 8, vdesc + (uint64_t)(k * 128), idesc_o,
+                         (cp.j | k) != 0);
+          }
+          umma_commit<1>(&o_done[i]);
+          umma_commit<1>(&kv_empty[slot]);
         }
-        umma_commit<1>(&o_done[i]);
-        umma_commit<1>(&kv_empty[slot]);
+        __syncwarp();
         ++n_p;
         advance(cp);
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax warpgroups
-    const int i = (warp - 3) >> 2;                    // query tile of this warpgroup
+    // ------------------------------------------------------------------ softmax warps
+    // SPLIT threads share one query row: thread `part` owns key columns [part*NC, part*NC + NC) of S / P and output
+    // dims [part*ND, part*ND + ND) of O.  With SPLIT = 2 there are 16 softmax warps (4 per scheduler instead of 2)
+    // to hide the MUFU / TMEM latencies; the row maximum and the final row sum are combined through shared memory.
+    constexpr int NC = KT / SPLIT, ND = HD / SPLIT;
+    const int sw = warp - 3;                          // softmax warp index
+    const int i = sw / (4 * SPLIT);                   // query tile
+    const int part = (sw >> 2) % SPLIT;               // column part of the row
     const int lg = warp & 3;                          // TMEM lane group this warp may access
     const int row = lg * 32 + lane;                   // query row inside the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
     const int DO = p.H * HD;
-    uint32_t s_cnt = 0, o_cnt = 0;
+    float* xch = reinterpret_cast<float*>(smem + kXchOff) + i * (2 * SPLIT * QT);   // [2 buffers][SPLIT][128 rows]
+    uint32_t s_cnt = 0, o_cnt = 0, x_cnt = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const Item it = decode_item(p, item);
       const int q = it.q0 + i * QT + row;
-      bf16* orow = p.out + ((long long)it.b * p.T + q) * DO + it.h * HD;
+      bf16* orow = p.out + ((long long)it.b * p.T + q) * DO + it.h * HD + part * ND;
       if (it.dead || i >= it.n_act) {                 // tile of padded queries: defined zero output
         if (q < p.T) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
+          for (int c = 0; c < ND / 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
         }
         continue;
       }
@@ -237,38 +277,43 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         mbar_wait(&s_full[i], s_cnt & 1);
         ++s_cnt;
         tc_fence_after();
-        uint32_t s[128];
+        uint32_t s[NC];
         {
-          uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-          uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-          uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
-          uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
-          const uint32_t sa = lane_addr + kColS + i * 128;
-          tmem_ld32(sa, s0); tmem_ld32(sa + 32, s1); tmem_ld32(sa + 64, s2); tmem_ld32(sa + 96, s3);
+          const uint32_t sa = lane_addr + kColS + i * 128 + part * NC;
+#pragma unroll
+          for (int c = 0; c < NC / 32; ++c) tmem_ld32(sa + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
           tmem_ld_wait();
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[i]);
-        const int valid = it.len - j * KT;             // > 0
-        if (valid < KT) {
+        const int valid = it.len - j * KT - part * NC;      // valid keys among this thread's columns (may be <= 0)
+        if (valid < NC) {
 #pragma unroll
-          for (int c = 0; c < 128; ++c) if (c >= valid) s[c] = 0xff800000u;   // -inf
+          for (int c = 0; c < NC; ++c) if (c >= valid) s[c] = 0xff800000u;   // -inf
         }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < 128; c += 4) {
+        for (int c = 0; c < NC; c += 4) {
           mx[0] = fmaxf(mx[0], __uint_as_float(s[c])); mx[1] = fmaxf(mx[1], __uint_as_float(s[c + 1]));
           mx[2] = fmaxf(mx[2], __uint_as_float(s[c + 2])); mx[3] = fmaxf(mx[3], __uint_as_float(s[c + 3]));
         }
-        const float mxl = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kLog2e;
+        float mxl = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kLog2e;
+        if constexpr (SPLIT > 1) {                    // combine the parts' maxima (double-buffered exchange slots)
+          float* slot = xch + (x_cnt & 1) * (SPLIT * QT);
+          ++x_cnt;
+          slot[part * QT + row] = mxl;
+          named_bar_sync(1 + i, 128 * SPLIT);
+#pragma unroll
+          for (int o = 0; o < SPLIT; ++o) mxl = fmaxf(mxl, slot[o * QT + row]);
+        }
         float scale = 1.0f;
         const bool grow = mxl > m_used + kRescaleThreshold;     // always true for j == 0 (m_used = -inf)
         if (grow) { scale = ex2(m_used - mxl); m_used = mxl; }   // j == 0: scale = 0, l = 0, O not yet written
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t pk[64];
+        uint32_t pk[NC / 2];
 #pragma unroll
-        for (int c = 0; c < 128; c += 4) {
+        for (int c = 0; c < NC; c += 4) {
           const float p0 = ex2(fmaf(__uint_as_float(s[c]), kLog2e, -m_used));
           const float p1 = ex2(fmaf(__uint_as_float(s[c + 1]), kLog2e, -m_used));
           const float p2 = ex2(fmaf(__uint_as_float(s[c + 2]), kLog2e, -m_used));
@@ -277,31 +322,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           pk[c >> 1] = pack2(p0, p1);
           pk[(c >> 1) + 1] = pack2(p2, p3);
         }
-        l = fmaf(l, scale, (sum[0] + sum[1]) + (sum[2] + sum[3]));
+        l = fmaf(l, scale, (sum[0] + sum[1]) + (sum[2] + sum[3]));   // this part's share of the row sum
         if (j > 0) {
           mbar_wait(&o_done[i], o_cnt & 1);             // P_i(j-1) V accumulated: P_i is free, O_i is stable
           ++o_cnt;
           tc_fence_after();
-          if (__any_sync(0xffffffffu, grow)) {
-            const uint32_t oa = lane_addr + kColO + i * 64;
+          if (__any_sync(0xffffffffu, grow)) {          // same rows, hence the same votes, in every part's warp
+            const uint32_t oa = lane_addr + kColO + i * 64 + part * ND;
+            uint32_t o[ND];
+            tmem_ld_n<ND>(oa, o);
+            tmem_ld_wait();
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint32_t o[32];
-              tmem_ld32(oa + half * 32, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * scale);
-              tmem_st32(oa + half * 32, o);
-            }
+            for (int c = 0; c < ND; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * scale);
+            tmem_st_n<ND>(oa, o);
           }
         }
         {
-          const uint32_t pa = lane_addr + kColP + i * 64;
+          const uint32_t pa = lane_addr + kColP + i * 64 + part * (NC / 2);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t(&chunk)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]);
-            tmem_st16(pa + c * 16, chunk);
-          }
+          for (int c = 0; c < NC / 32; ++c) tmem_st16(pa + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]));
           tmem_st_wait();
         }
         tc_fence_before();
@@ -312,21 +351,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
       mbar_wait(&o_done[i], o_cnt & 1);
       ++o_cnt;
       tc_fence_after();
-      uint32_t o[64];
-      {
-        uint32_t(&o0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&o[0]);
-        uint32_t(&o1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&o[32]);
-        const uint32_t oa = lane_addr + kColO + i * 64;
-        tmem_ld32(oa, o0); tmem_ld32(oa + 32, o1);
-        tmem_ld_wait();
-      }
+      uint32_t o[ND];
+      tmem_ld_n<ND>(lane_addr + kColO + i * 64 + part * ND, o);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[i]);
+      if constexpr (SPLIT > 1) {                        // total row sum over the parts
+        float* slot = xch + (x_cnt & 1) * (SPLIT * QT);
+        ++x_cnt;
+        slot[part * QT + row] = l;
+        named_bar_sync(1 + i, 128 * SPLIT);
+        l = 0.f;
+#pragma unroll
+        for (int o2 = 0; o2 < SPLIT; ++o2) l += slot[o2 * QT + row];
+      }
       const float inv = (q < it.len && l > 0.f) ? 1.0f / l : 0.f;     // padded query rows -> 0
       if (q < p.T) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < ND / 8; ++c) {
           uint4 u;
           u.x = pack2(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
           u.y = pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
@@ -362,14 +405,17 @@ int attention_tc(const bf16* qkv, bf16* out, const long long* lens, int nb, int 
   p.lens = lens; p.out = out; p.T = T; p.H = H; p.nb = nb;
   p.n_qp = ceil_div(T, 2 * QT);
   p.n_items = p.n_qp * H * nb;
+  static const int split = [] { const char* e = getenv("SWC_ATTN_SPLIT"); return (e && e[0] == '1') ? 1 : 2; }();
   static bool configured = false;
   if (!configured) {
-    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
   const int grid = std::min(p.n_items, num_sms);
   ProfScope ps(KC_ATTN, s);
-  attention_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(tm, p);
+  if (split == 1) attention_tc_kernel<1><<<grid, 96 + 256, kSmemBytes, s>>>(tm, p);
+  else attention_tc_kernel<2><<<grid, 96 + 512, kSmemBytes, s>>>(tm, p);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

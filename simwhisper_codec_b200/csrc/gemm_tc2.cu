@@ -151,7 +151,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   if constexpr (CG > 1) cluster_sync();      // peer barriers are initialised before any remote arrive / TMA completion
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   const int cid = blockIdx.x / CG, ncl = gridDim.x / CG;
   const int tiles_per_batch = p.m_tiles * p.n_tiles;
@@ -159,29 +159,32 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_kb = p.n_taps * p.kb_per_tap;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = cid; tile < total_tiles; tile += ncl) {
-        const int b = tile / tiles_per_batch;
-        const int r = tile - b * tiles_per_batch;
-        const int m0 = (r / p.n_tiles) * (BM * CG) + (int)rank * BM;
-        const int n0 = (r % p.n_tiles) * BN + (int)rank * (BN / CG);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;
-          mbar_wait(&empty[stage], phase ^ 1);
+    // whole warp runs the loop (uniform control flow); one elected lane issues the TMA instructions
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cid; tile < total_tiles; tile += ncl) {
+      const int b = tile / tiles_per_batch;
+      const int r = tile - b * tiles_per_batch;
+      const int m0 = (r / p.n_tiles) * (BM * CG) + (int)rank * BM;
+      const int n0 = (r % p.n_tiles) * BN + (int)rank * (BN / CG);
+      int tap = 0, kc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           // all bytes of the pair land on the leader's barrier; the leader alone arrives (expect_tx of both halves)
           const uint32_t bar = CG == 1 ? smem_u32(&full[stage]) : mapa(smem_u32(&full[stage]), 0);
           if (leader) mbar_expect_tx(&full[stage], CG * L::kStageBytes);
           uint8_t* sa = smem + stage * L::kStageBytes;
           tma_load_3d<CG>(&tmA, bar, sa, p.tap_col[tap] + kc * BK, m0 + p.tap_row[tap], b);
           tma_load_2d<CG>(&tmW, bar, sa + L::kABytes, kb * BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++kc == p.kb_per_tap) { kc = 0; ++tap; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
       constexpr uint32_t idesc = make_idesc(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -197,15 +200,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
           const uint64_t adesc = make_smem_desc(sa);
           const uint64_t bdesc = make_smem_desc(sa + L::kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (>>4) address field
-            umma_bf16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (>>4) address field
+              umma_bf16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
+            umma_commit<CG>(&empty[stage]);
+            if (kb == num_kb - 1) umma_commit<CG>(&tfull[acc]);
           }
-          umma_commit<CG>(&empty[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit<CG>(&tfull[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

@@ -28,6 +28,21 @@ __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
   return r;
 }
 
+// one lane of a fully active warp (the same lane on every call).  Used to issue TMA / tcgen05 instructions from warp-
+// uniform code: when the surrounding control flow is uniform the compiler keeps descriptors, addresses and coordinates
+// in uniform registers, whereas code under `if (lane == 0)` pays an ELECT + R2UR.BROADCAST loop per instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// broadcast lane 0's value: marks a value read from shared memory as warp-uniform for the compiler
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---- mbarrier ------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -14,10 +14,12 @@ from simwhisper_codec_b200 import _lib  # noqa: E402
 def main():
     lib = _lib.load()
     backends = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["2", "3"])]
-    B, T, H = int(os.environ.get("AB_B", 64)), 1500, 12
+    B, T, H = int(os.environ.get("AB_B", 64)), int(os.environ.get("AB_T", 1500)), 12
     reps = int(os.environ.get("AB_REPS", 5))
     g = torch.Generator(device="cuda").manual_seed(1)
-    qkv = (torch.randn(B, T, 3 * H * 64, device="cuda", generator=g) * 0.7).bfloat16()
+    qkv = torch.randn(B, T, 3 * H * 64, device="cuda", generator=g) * 0.7
+    qkv[..., : H * 64] *= 0.125          # the packed q_proj carries the 1/sqrt(head_dim) scale
+    qkv = qkv.bfloat16()
     lens = torch.full((B,), T, device="cuda", dtype=torch.int64)
     out = torch.empty(B, T, H * 64, device="cuda", dtype=torch.bfloat16)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -40,7 +42,7 @@ def main():
         err = 0.0 if ref is None else float((o - ref).abs().max())
         if ref is None:
             ref = o
-        print(json.dumps({"backend": be, "B": B, "ms": round(ms, 4), "tflops": round(4.0 * B * H * T * T * 64 / ms / 1e9, 1),
+        print(json.dumps({"backend": be, "B": B, "T": T, "ms": round(ms, 4), "tflops": round(4.0 * B * H * T * T * 64 / ms / 1e9, 1),
                           "max_abs_diff_vs_first": err}), flush=True)
 
 
