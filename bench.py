@@ -34,6 +34,8 @@ GF_TOTAL = 1311.86
 GF_ATTN = 24 * 6.912
 GF_MEL = 1.061
 GF_IDFT = 2.465
+# DRAM traffic of the tcgen05 GEMM class per window, from the committed ncu launch list (profiles/r1_ncu_launches_v4.md)
+GEMM_DRAM_GB_PER_WINDOW = 2.30
 GF_TC_GEMM = GF_TOTAL - GF_ATTN - GF_MEL              # contractions that run on the tcgen05 GEMM kernels (the inverse DFT
                                                        # included: it runs as a 3-product split-bf16 GEMM, counted once)
 
@@ -244,9 +246,12 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PF/s sustained (B200_PROFILING.md)"
     gemm_ms = cls_ms["gemm_tcgen05"]
     achieved = (GF_TC_GEMM * B / 1e3) / (gemm_ms * 1e-3) if gemm_ms > 0 else 0.0
-    roofline = {"kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all instantiations)", "bound": "tensor",
+    roofline = {"kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16 GEMMs, all instantiations)", "bound": "tensor",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": GEMM_DRAM_GB_PER_WINDOW * 1e9 * B / max(cls_n["gemm_tcgen05"], 1),
+                "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of the gemm_tc* launches of one "
+                                "step under ncu, profiles/r1_ncu_launches_v4.md, averaged per launch)",
+                "peak_source": peak_src,
                 "algorithmic_gflop_per_window": GF_TC_GEMM, "windows_per_step": B, "launches_per_step": cls_n["gemm_tcgen05"],
                 "avg_launch_ms": gemm_ms / max(cls_n["gemm_tcgen05"], 1),
                 "class_ms_per_step": cls_ms, "class_share": {k: v / tot_cls for k, v in cls_ms.items()},
