@@ -159,6 +159,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0 must print exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off stdout
+        if not os.environ.get("SWC_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     gp = gen_params()
