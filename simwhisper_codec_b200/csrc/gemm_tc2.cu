@@ -1,6 +1,6 @@
 // bf16 tcgen05 GEMM, second generation: CTA-pair MMA (cta_group::2) and TMA-store epilogue.
 //
-//   D[b, m, n] = act(sum_tap sum_k A[b, m + tap_row, tap_col + k] * W[n, tap*tap_k + k] + bias[n]) * gamma[n]
+//   D[b, m, n] (+)= act(sum_tap sum_k A[b, m + tap_row, tap_col + k] * W[n, tap*tap_k + k] + bias[n]) * gamma[n]
 //
 // One cluster of CG CTAs (CG = 2: the two SMs of a TPC) owns a (128*CG) x 256 output tile.  Each CTA stages its
 // own 128 rows of A and its 256/CG rows of W per 64-wide K slab, so with CG = 2 the pair reads every W slab
@@ -118,7 +118,7 @@ __device__ __forceinline__ void epi4(const uint32_t* acc, const float* sb, const
   }
 }
 
-template <int CG, int STAGES, int NBUF, int ACT, bool GAMMA, typename TO>
+template <int CG, int STAGES, int NBUF, int ACT, bool GAMMA, bool REDUCE, typename TO>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmO, const Tc2Params p) {
@@ -280,7 +280,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) {
             const int col = n0 + c_base + (kF32 ? sub * 32 : (sub >> 1) * 64);
-            tma_store_3d(&tmO, stage_out + obuf * L::kOutBytesPerWarp, col, m0 + lg * 32, b);
+            // REDUCE: the residual add out += tile is done by the L2 (one tile per output element: deterministic)
+            if constexpr (REDUCE) tma_reduce_add_3d(&tmO, stage_out + obuf * L::kOutBytesPerWarp, col, m0 + lg * 32, b);
+            else tma_store_3d(&tmO, stage_out + obuf * L::kOutBytesPerWarp, col, m0 + lg * 32, b);
             tma_store_commit();
           }
           obuf = (obuf + 1 == NBUF) ? 0 : obuf + 1;
@@ -301,7 +303,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int CG, int STAGES, int NBUF, int ACT, bool GAMMA, typename TO>
+template <int CG, int STAGES, int NBUF, int ACT, bool GAMMA, bool REDUCE, typename TO>
 int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
   using L = Smem2<CG, STAGES, NBUF>;
   constexpr int out_type = sizeof(TO) == 4 ? 0 : 1;
@@ -335,7 +337,7 @@ int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
   p.n_taps = d.n_taps; p.kb_per_tap = d.tap_k / BK;
   for (int i = 0; i < d.n_taps; ++i) { p.tap_row[i] = d.tap_row[i]; p.tap_col[i] = d.tap_col[i]; }
   p.bias = d.epi.bias; p.gamma = d.epi.gamma;
-  auto kern = gemm_tc2_kernel<CG, STAGES, NBUF, ACT, GAMMA, TO>;
+  auto kern = gemm_tc2_kernel<CG, STAGES, NBUF, ACT, GAMMA, REDUCE, TO>;
   static bool configured = false;
   if (!configured) {
     SWC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -361,13 +363,19 @@ template <int CG, int STAGES, int NBUF>
 int dispatch2(const GemmDesc& d, int out_type, int num_sms, cudaStream_t s) {
   const int act = d.epi.act;
   const bool gamma = d.epi.gamma != nullptr;
+  const bool reduce = d.epi.residual != nullptr;      // eligibility guarantees residual == out (fp32, same addressing)
   if (out_type == 0) {
-    if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, 0, false, float>(d, num_sms, s);
-    if (act == 0 && gamma) return launch2<CG, STAGES, NBUF, 0, true, float>(d, num_sms, s);
-    if (act == 2 && !gamma) return launch2<CG, STAGES, NBUF, 2, false, float>(d, num_sms, s);
-  } else {
-    if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, 0, false, bf16>(d, num_sms, s);
-    if (act == 2 && !gamma) return launch2<CG, STAGES, NBUF, 2, false, bf16>(d, num_sms, s);
+    if (reduce) {
+      if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, 0, false, true, float>(d, num_sms, s);
+      if (act == 0 && gamma) return launch2<CG, STAGES, NBUF, 0, true, true, float>(d, num_sms, s);
+    } else {
+      if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, 0, false, false, float>(d, num_sms, s);
+      if (act == 0 && gamma) return launch2<CG, STAGES, NBUF, 0, true, false, float>(d, num_sms, s);
+      if (act == 2 && !gamma) return launch2<CG, STAGES, NBUF, 2, false, false, float>(d, num_sms, s);
+    }
+  } else if (!reduce) {
+    if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, 0, false, false, bf16>(d, num_sms, s);
+    if (act == 2 && !gamma) return launch2<CG, STAGES, NBUF, 2, false, false, bf16>(d, num_sms, s);
   }
   set_error("gemm_tc2: unsupported epilogue (act %d, gamma %d, out type %d)", act, (int)gamma, out_type);
   return -1;
@@ -379,7 +387,11 @@ int dispatch2(const GemmDesc& d, int out_type, int num_sms, cudaStream_t s) {
 bool gemm_tc2_eligible(const GemmDesc& d) {
   const EpiParams& e = d.epi;
   if (e.gamma && e.act != 0) return false;       // gamma only accompanies the plain fp32 pwconv2 epilogue
-  return e.residual == nullptr && e.out2 == nullptr && (e.act == 0 || e.act == 2) && d.N >= 256 && d.N % 8 == 0 &&
+  // a residual is taken only as an in-place accumulation out += tile (TMA reduce-add), never as a separate operand
+  if (e.residual && (e.residual != e.out || e.act != 0 || e.res_row_stride != e.out_row_stride * e.out_row_mul ||
+                     e.out_row_off != 0 || (d.nb > 1 && e.res_batch_stride != e.out_batch_stride)))
+    return false;
+  return e.out2 == nullptr && (e.act == 0 || e.act == 2) && d.N >= 256 && d.N % 8 == 0 &&
          d.tap_k % BK == 0 && ((uintptr_t)e.out & 15) == 0;
 }
 

@@ -69,10 +69,10 @@ int run_attention(Ctx& c, const void* qkv, void* out, const long long* lens, int
 // ------------------------------------------------------------------------------------------------
 // transformer stack shared by encoder and decoder (reference modules.py:214-232), h fp32 (nb,T,768)
 // ------------------------------------------------------------------------------------------------
-// Each sub-layer's GEMM writes its (bias-added) output as an fp32 delta; the residual add is fused into the
-// LayerNorm that follows (h <- h + delta, xn = LN(h)).  On return the last fc2 delta is still pending in
-// `delta`: the caller's final LayerNorm consumes it.
-int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, float* delta, const long long* lens, int nb, int T) {
+// Each sub-layer's output GEMM accumulates straight into the fp32 residual stream: h += out_proj(...) / h += fc2(...)
+// (bf16 mode: the epilogue's TMA store is a reduce-add performed by the L2; fp32 mode: the SIMT epilogue reads and
+// writes h in place).  LayerNorm then only reads h and writes the normalised operand of the next GEMM.
+int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const long long* lens, int nb, int T) {
   const Model& m = *c.m;
   const int D = m.d_model, at = m.act_type();
   const int gelu = at == 1 ? 2 : 1;
@@ -85,7 +85,7 @@ int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, float
   SWC_TRY(c.ws.check());
   for (size_t li = 0; li < layers.size() && !c.dry; ++li) {
     const LayerW& L = layers[li];
-    SWC_TRY(layernorm(h, li ? delta : nullptr, li ? h : nullptr, xn, at, L.ln1_g, L.ln1_b, 1e-5f, nb, T, T, D, nullptr, c.s));
+    SWC_TRY(layernorm(h, nullptr, nullptr, xn, at, L.ln1_g, L.ln1_b, 1e-5f, nb, T, T, D, nullptr, c.s));
     {
       GemmDesc d = base_desc(xn, D, 0, (int)rows, D, (int)rows, 1, L.qkv);
       set_out(d, qkv, 3 * D, 0);
@@ -94,10 +94,11 @@ int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, float
     SWC_TRY(run_attention(c, qkv, ao, lens, nb, T));
     {
       GemmDesc d = base_desc(ao, D, 0, (int)rows, D, (int)rows, 1, L.out);
-      set_out(d, delta, D, 0);
+      set_out(d, h, D, 0);
+      d.epi.residual = h; d.epi.res_row_stride = D;
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
     }
-    SWC_TRY(layernorm(h, delta, h, xn, at, L.ln2_g, L.ln2_b, 1e-5f, nb, T, T, D, nullptr, c.s));
+    SWC_TRY(layernorm(h, nullptr, nullptr, xn, at, L.ln2_g, L.ln2_b, 1e-5f, nb, T, T, D, nullptr, c.s));
     {
       GemmDesc d = base_desc(xn, D, 0, (int)rows, D, (int)rows, 1, L.fc1);
       set_out(d, ff, m.ffn, 0);
@@ -106,7 +107,8 @@ int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, float
     }
     {
       GemmDesc d = base_desc(ff, m.ffn, 0, (int)rows, m.ffn, (int)rows, 1, L.fc2);
-      set_out(d, delta, D, 0);
+      set_out(d, h, D, 0);
+      d.epi.residual = h; d.epi.res_row_stride = D;
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
     }
   }
@@ -125,7 +127,6 @@ int encoder_cl(Ctx& c, const void* mel_cl, const long long* enc_lens, int nb, in
   const size_t mark = c.ws.mark();
   void* stem = c.ws.alloc((long long)nb * 2 * T * D * esz(at));
   float* h = (float*)c.ws.alloc((long long)nb * T * D * 4);
-  float* delta = (float*)c.ws.alloc((long long)nb * T * D * 4);
   SWC_TRY(c.ws.check());
   if (!c.dry) {
     if (Tm & 1) SWC_CHECK_CUDA(cudaMemsetAsync(stem, 0, (size_t)nb * 2 * T * D * esz(at), c.s));
@@ -146,8 +147,8 @@ int encoder_cl(Ctx& c, const void* mel_cl, const long long* enc_lens, int nb, in
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
     }
   }
-  SWC_TRY(transformer_stack(c, m.enc_layers, h, delta, enc_lens, nb, T));
-  if (!c.dry) SWC_TRY(layernorm(h, delta, nullptr, enc_cl, at, m.enc_ln_g, m.enc_ln_b, 1e-5f, nb, T, T4, D, enc_lens, c.s));
+  SWC_TRY(transformer_stack(c, m.enc_layers, h, enc_lens, nb, T));
+  if (!c.dry) SWC_TRY(layernorm(h, nullptr, nullptr, enc_cl, at, m.enc_ln_g, m.enc_ln_b, 1e-5f, nb, T, T4, D, enc_lens, c.s));
   c.ws.release(mark);
   return 0;
 }
@@ -247,14 +248,12 @@ int decoder_cl(Ctx& c, float* h, const long long* lens, int nb, int T, void* mel
   const Model& m = *c.m;
   const int D = m.d_model, MP = m.mel_pitch, at = m.act_type();
   const size_t mark = c.ws.mark();
-  float* delta = (float*)c.ws.alloc((long long)nb * T * D * 4);
-  SWC_TRY(c.ws.check());
-  SWC_TRY(transformer_stack(c, m.dec_layers, h, delta, lens, nb, T));
+  SWC_TRY(transformer_stack(c, m.dec_layers, h, lens, nb, T));
   void* y = c.ws.alloc((long long)nb * T * D * esz(at));
   void* z = c.ws.alloc((long long)nb * 2 * T * D * esz(at));
   SWC_TRY(c.ws.check());
   if (!c.dry) {
-    SWC_TRY(layernorm(h, delta, nullptr, y, at, m.dec_ln_g, m.dec_ln_b, 1e-5f, nb, T, T, D, lens, c.s));
+    SWC_TRY(layernorm(h, nullptr, nullptr, y, at, m.dec_ln_g, m.dec_ln_b, 1e-5f, nb, T, T, D, lens, c.s));
     {   // deconv1 even output rows 2t: taps h[t-1] (k=2), h[t] (k=0)
       GemmDesc d = base_desc(y, D, (long long)T * D, T, D, T, nb, m.deconv1_even);
       d.n_taps = 2; d.tap_k = D;
@@ -291,9 +290,7 @@ int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav) {
   const long long rows = (long long)nb * Tv;
   const int NP = m.voc_head.N;
   const size_t mark = c.ws.mark();
-  float* xa = (float*)c.ws.alloc(rows * V * 4);      // residual stream, ping-pong (the fused add cannot be in place)
-  float* xb = (float*)c.ws.alloc(rows * V * 4);
-  float* delta = (float*)c.ws.alloc(rows * V * 4);   // gamma * (pwconv2 + bias) of the previous block
+  float* x = (float*)c.ws.alloc(rows * V * 4);       // fp32 residual stream; pwconv2 accumulates into it (x += gamma * (...))
   void* y = c.ws.alloc(rows * V * esz(at));
   // the 4096-wide hidden, the spectrum and the frames are never live together: share one region
   const size_t big = std::max<size_t>((size_t)rows * I * esz(at), (size_t)rows * (NP + m.n_fft) * 4);
@@ -309,13 +306,9 @@ int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav) {
       set_out(d, e, V, (long long)Tv * V);
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
     }
-    float* x = xa;
-    float* xn = xb;
     SWC_TRY(layernorm(e, nullptr, nullptr, x, 0, m.voc_norm_g, m.voc_norm_b, 1e-6f, nb, Tv, Tv, V, nullptr, c.s));
-    bool pending = false;
     for (const VocosBlockW& B : m.voc_blocks) {
-      SWC_TRY(dwconv7_ln(x, pending ? delta : nullptr, pending ? xn : nullptr, B.dw_w, B.dw_b, B.ln_g, B.ln_b, 1e-6f, y, at, nb, Tv, V, c.s));
-      if (pending) std::swap(x, xn);
+      SWC_TRY(dwconv7_ln(x, nullptr, nullptr, B.dw_w, B.dw_b, B.ln_g, B.ln_b, 1e-6f, y, at, nb, Tv, V, c.s));
       {
         GemmDesc d = base_desc(y, V, 0, (int)rows, V, (int)rows, 1, B.pw1);
         set_out(d, g, I, 0);
@@ -324,13 +317,13 @@ int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav) {
       }
       {
         GemmDesc d = base_desc(g, I, 0, (int)rows, I, (int)rows, 1, B.pw2);
-        set_out(d, delta, V, 0);
+        set_out(d, x, V, 0);
         d.epi.gamma = B.gamma;
+        d.epi.residual = x; d.epi.res_row_stride = V;
         SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
       }
-      pending = true;
     }
-    SWC_TRY(layernorm(x, pending ? delta : nullptr, nullptr, y, at, m.voc_final_g, m.voc_final_b, 1e-6f, nb, Tv, Tv, V, nullptr, c.s));
+    SWC_TRY(layernorm(x, nullptr, nullptr, y, at, m.voc_final_g, m.voc_final_b, 1e-6f, nb, Tv, Tv, V, nullptr, c.s));
     float* S = (float*)region;
     float* frames = S + rows * NP;
     const bool tc_idft = at == 1 && !c.force_simt && m.w_idft3 != nullptr;

@@ -35,7 +35,7 @@ struct Ctx {
   bool force_simt = false;   // debugging: run bf16 operands through the SIMT kernels
 };
 
-int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, float* delta, const long long* lens, int nb, int T);
+int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const long long* lens, int nb, int T);
 int encoder_cl(Ctx& c, const void* mel_cl, const long long* enc_lens, int nb, int Tm, void* enc_cl);
 int downsample_fsq(Ctx& c, const void* enc_cl, const long long* code_lens, int nb, int T4, int* codes, float* zq_cf,
                    float* latent_cf, float* zq_cl);
