@@ -284,7 +284,16 @@ __global__ void __launch_bounds__(128) aa_snake_kernel(const TI* __restrict__ in
       acc = fmaf(xv, tap, acc);
     }
     const float u = 2.0f * acc;
-    const float sn = sinf(u * ea);
+    float sn;
+    if constexpr (sizeof(TO) == 2) {
+      // bf16 output: two-constant Cody-Waite reduction to [-pi, pi] + MUFU.SIN (abs error ~2^-21, far below bf16 rounding)
+      const float a = u * ea;
+      const float k = rintf(a * 0.15915494309189535f);
+      const float r = fmaf(k, 1.7484555e-7f, fmaf(k, -6.2831855f, a));   // a - k*2pi with 2pi = 6.2831855f - 1.7484555e-7f
+      sn = __sinf(r);
+    } else {
+      sn = sinf(u * ea);
+    }
     return u + inv_b * (sn * sn);
   };
 
