@@ -137,3 +137,57 @@ def test_full_window_properties_fp32(model32):
     solo = model32.inference_tokenize(x[2:3], lens[2:3])
     assert torch.equal(solo["codes"][:, 0], r["codes"][:, 2])          # encode is batch independent
     assert int(r["codes"][:, 3, 25:].abs().max()) == 0
+
+
+def test_full_window_vs_oracle_fp32(model32, sd_ex):
+    """One full 30 s window (BASELINE configs[1]/[2] item size) against the CPU oracle on the same weights and input:
+    indices bit-exact up to near-tie flips < 0.1 %, waveform SNR >= 40 dB on identical codes."""
+    w = synthetic_wave(4000, 480000)
+    x = w[None, None, :]
+    lens = torch.tensor([480000])
+    with torch.inference_mode():
+        ref = port.tokenize(sd_ex, x, lens)
+        ref_wav = port.detokenize(sd_ex, ref["codes"], ref["codes_lengths"])
+    r = model32.inference_tokenize(x.cuda(), lens.cuda())
+    assert r["codes"].shape == (8, 1, 375)
+    flips = (r["codes"].cpu() != ref["codes"]).float().mean().item()
+    assert flips < 1e-3, flips
+    out = model32.inference_detokenize(ref["codes"].cuda(), ref["codes_lengths"].cuda())
+    assert int(out["output_length"][0]) == 480000
+    assert snr_db(ref_wav["y"], out["y"].cpu()) >= 40.0
+
+
+def test_bf16_full_window_properties(model16, model32, gen_params, sd_ex):
+    """bf16 (tcgen05) mode at full window size: batch independence, sub-batch independence, and its distance from the
+    fp32 path on the same device (reported; loose bounds)."""
+    n = [480000, 479841, 240000, 100000, 480000]
+    w = [synthetic_wave(5000 + i, k).cuda() for i, k in enumerate(n)]
+    x = torch.zeros(len(n), 1, 480000, device="cuda")
+    for i, wi in enumerate(w):
+        x[i, 0, : wi.numel()] = wi
+    lens = torch.tensor(n, device="cuda")
+    r = model16.inference_tokenize(x, lens)
+    assert r["codes_lengths"].tolist() == [375, 375, 188, 78, 375]
+    # every item's codes do not depend on what it is batched with, nor on how the batch is split into launches
+    solo = model16.inference_tokenize(x[2:3], lens[2:3])
+    assert torch.equal(solo["codes"][:, 0], r["codes"][:, 2])
+    small = AudioCodec(gen_params, precision="bf16", max_batch=2)
+    small.load_state_dict(sd_ex)
+    r2 = small.inference_tokenize(x, lens)
+    assert torch.equal(r2["codes"], r["codes"])
+    for b, k in enumerate(r["codes_lengths"].tolist()):
+        assert int(r["codes"][:, b, k:].abs().max()) == 0 if k < 375 else True
+    # against the fp32 path
+    r32 = model32.inference_tokenize(x, lens)
+    valid = torch.arange(375, device="cuda")[None, None, :] < r["codes_lengths"][None, :, None]
+    flips = ((r["codes"] != r32["codes"]) & valid).sum().item() / (8 * int(r["codes_lengths"].sum()))
+    print(f"bf16 vs fp32 (same device) index flip rate on 30 s windows: {flips:.4f}")
+    assert flips < 0.25
+    y16 = model16.inference_detokenize(r32["codes"], r32["codes_lengths"])
+    y32 = model32.inference_detokenize(r32["codes"], r32["codes_lengths"])
+    assert y16["output_length"].tolist() == y32["output_length"].tolist() == [480000, 480000, 240640, 99840, 480000]
+    s = snr_db(y32["y"][0, 0].cpu(), y16["y"][0, 0].cpu())
+    print(f"bf16 vs fp32 decode SNR (same codes, 30 s): {s:.1f} dB")
+    assert s > 30.0
+    y2 = small.inference_detokenize(r32["codes"], r32["codes_lengths"])
+    assert torch.equal(y2["y"], y16["y"])
