@@ -215,9 +215,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         skip_inactive(cs);
       };
       skip_inactive(cs);
-      if (cs.item < p.n_items) issue_s();                        // S runs one key block ahead of P V
       while (cp.item < p.n_items) {
         const uint32_t slot = cp.g % STAGES;
+        // S runs at most one ring entry ahead of the P V cursor.  (Never further: the producer can only fill a slot
+        // once BOTH issuers have released the entry STAGES before it, and this issuer releases in cursor order.)
+        while (cs.item < p.n_items && cs.g <= cp.g + 1) issue_s();
         if (!cp.active) {
           // this tile sits the item out but still owes the ring its release: in ring order, once the slot has landed
           mbar_wait(&kv_full[slot], (cp.g / STAGES) & 1);
@@ -226,7 +228,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           advance(cp);
           continue;
         }
-        if (cs.item < p.n_items) issue_s();
         mbar_wait(&p_full[i], n_p & 1);
         if (cp.j == 0) mbar_wait(&o_free[i], (cp.n_items & 1) ^ 1);   // the previous item's O_i has been read out
         tc_fence_after();

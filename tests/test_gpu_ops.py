@@ -120,3 +120,28 @@ def test_attention_growing_maximum(backend):
     ok = torch.arange(T, device="cuda")[None, :] < lens_t[:, None]
     diff = ((out.double() - ref) * ok[..., None]).abs().max().item()
     assert diff < 2e-2, diff
+
+
+@pytest.mark.parametrize("backend", [2, 3])
+def test_attention_many_items_mixed_lengths(backend):
+    """More work items than SMs with every kind of item mixed on one persistent CTA: full tiles, tiles whose second
+    128-query half is padding, fully padded (dead) tiles, one-key sequences and empty sequences."""
+    lib = _lib.load()
+    B, T, H = 40, 1500, 12
+    g = torch.Generator().manual_seed(11)
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    lens[:8] = torch.tensor([1500, 1, 0, 128, 129, 256, 257, 1407])
+    qkv = torch.randn(B, T, 3 * H * 64, generator=g) * 0.7
+    qkv[..., : H * 64] *= 0.125
+    qkv = qkv.bfloat16().cuda()
+    lens_t = lens.to(device="cuda", dtype=torch.int64)
+    out = torch.full((B, T, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.swc_test_attention(backend, _p(qkv), _p(out), _p(lens_t), B, T, H, _stream()), "attention")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    ok = torch.arange(T, device="cuda")[None, :] < lens_t[:, None]
+    assert float(out.float().abs().amax(dim=-1)[~ok].max()) == 0.0           # padded query rows are zeros
+    for b in (0, 1, 3, 4, 6, 7, 20, 39):                                      # reference on a subset (memory)
+        ref = _attn_ref(qkv[b:b + 1], lens_t[b:b + 1], H)
+        diff = ((out[b:b + 1].double() - ref) * ok[b:b + 1, :, None]).abs().max().item()
+        assert diff < 2e-2, (b, int(lens[b]), diff)
