@@ -114,6 +114,17 @@ int swc_detokenize(const swc_model* m, const void* codes, int codes_are_int64, c
                    int code_frames, float* wav, int64_t* out_lens, void* workspace, size_t ws_bytes,
                    void* stream);
 
+/* ---- the same two chains when the caller also knows the lengths on the HOST (AudioCodec.encode()/decode() do:
+ *      model.py:262-268, 327-333 build them from Python lists).  In bf16 mode the two transformer stacks then run on the
+ *      packed valid tokens only (padded tokens of a window are skipped); results are bit-identical to swc_tokenize /
+ *      swc_detokenize.  host_lengths[b] must equal lengths[b]; batches above 128 items fall back to the padded path. ---- */
+int swc_tokenize_ragged(const swc_model* m, const float* wav, int64_t wav_stride, int wav_cols, const int64_t* lengths,
+                        const int64_t* host_lengths, int batch, int32_t* codes, float* zq_cf, int64_t* codes_lens,
+                        void* workspace, size_t ws_bytes, void* stream);
+int swc_detokenize_ragged(const swc_model* m, const void* codes, int codes_are_int64, const int64_t* lens,
+                          const int64_t* host_lens, int batch, int code_frames, float* wav, int64_t* out_lens,
+                          void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- AudioCodec.forward (model.py:112-165): mel_cf (B,80,Tm) -> audio (B, 160*8*ceil(ceil(Tm/2)/4)) ---- */
 int swc_forward(const swc_model* m, const float* mel_cf, const int64_t* mel_lens, int batch, int mel_frames,
                 float* wav, int64_t* out_lens, int32_t* codes /* optional (8,B,Tc) */, void* workspace,

@@ -40,6 +40,8 @@ SIGNATURES = {
     "swc_vocos": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
     "swc_tokenize": (_i, [_p, _p, _i64, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "swc_detokenize": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "swc_tokenize_ragged": (_i, [_p, _p, _i64, _i, _p, C.POINTER(_i64), _i, _p, _p, _p, _p, _sz, _p]),
+    "swc_detokenize_ragged": (_i, [_p, _p, _i, _p, C.POINTER(_i64), _i, _i, _p, _p, _p, _sz, _p]),
     "swc_forward": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "swc_profile": (None, [_i]),
     "swc_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(_i64), _i]),

@@ -29,6 +29,8 @@ import yaml
 from .. import _lib, windows
 from ..weights import state_dict_schema
 
+# encode()/decode() know every window's length on the host: skip padded tokens in the transformer stacks (bf16 mode).
+_RAGGED = os.environ.get("SWC_RAGGED", "1") != "0"
 _BUFFER_LEAVES = ("positional_embedding", "filter", "window", "dim_base_index", "num_levels")
 
 
@@ -242,7 +244,7 @@ class AudioCodec(nn.Module):
         self.precision = precision or os.environ.get("SWC_PRECISION", "fp32")
         if self.precision not in _lib.PRECISION:
             raise ValueError(f"precision must be one of {list(_lib.PRECISION)}, got {self.precision}")
-        self.max_batch = int(max_batch or os.environ.get("SWC_MAX_BATCH", 32))
+        self.max_batch = int(max_batch or os.environ.get("SWC_MAX_BATCH", 64))
 
         self.acoustic_encoder = OmniAudioEncoder(self, "encoder")
         self.downsample = FrameStackDownConv(self, "downsample")
@@ -323,8 +325,9 @@ class AudioCodec(nn.Module):
                                    _ptr(mel_lens), ws, nws, _stream()), "swc_mel")
         return mel, mel_lens
 
-    def _tokenize(self, x2d: torch.Tensor, lens: torch.Tensor, want_zq: bool):
-        """x2d (N, L<=480000) fp32 cuda, lens (N,) int64 cuda -> codes (8,N,375) int32, zq, code lens."""
+    def _tokenize(self, x2d: torch.Tensor, lens: torch.Tensor, want_zq: bool, host_lens=None):
+        """x2d (N, L<=480000) fp32 cuda, lens (N,) int64 cuda -> codes (8,N,375) int32, zq, code lens.
+        host_lens (Python ints, when the caller knows them) lets the bf16 path skip the padded tokens of every window."""
         nat = self._native_for(x2d.device)
         N = x2d.shape[0]
         codes = torch.empty((8, N, 375), dtype=torch.int32, device=x2d.device)
@@ -336,14 +339,20 @@ class AudioCodec(nn.Module):
             ws, nws = nat.workspace("tokenize", n, 3000)
             c_part = codes if N <= mb else torch.empty((8, n, 375), dtype=torch.int32, device=x2d.device)
             z_part = None if zq is None else zq[s:s + n]
-            _lib.check(nat.lib.swc_tokenize(nat.handle, _ptr(x2d[s:s + n]), x2d.stride(0), x2d.shape[1], _ptr(lens[s:s + n]),
-                                            n, _ptr(c_part), _ptr(z_part), _ptr(clens[s:s + n]), ws, nws, _stream()),
-                       "swc_tokenize")
+            if host_lens is not None and _RAGGED:
+                hl = (C.c_int64 * n)(*[int(v) for v in host_lens[s:s + n]])
+                _lib.check(nat.lib.swc_tokenize_ragged(nat.handle, _ptr(x2d[s:s + n]), x2d.stride(0), x2d.shape[1],
+                                                       _ptr(lens[s:s + n]), hl, n, _ptr(c_part), _ptr(z_part),
+                                                       _ptr(clens[s:s + n]), ws, nws, _stream()), "swc_tokenize_ragged")
+            else:
+                _lib.check(nat.lib.swc_tokenize(nat.handle, _ptr(x2d[s:s + n]), x2d.stride(0), x2d.shape[1], _ptr(lens[s:s + n]),
+                                                n, _ptr(c_part), _ptr(z_part), _ptr(clens[s:s + n]), ws, nws, _stream()),
+                           "swc_tokenize")
             if N > mb:
                 codes[:, s:s + n] = c_part
         return codes, zq, clens
 
-    def _detokenize(self, codes: torch.Tensor, lens: torch.Tensor):
+    def _detokenize(self, codes: torch.Tensor, lens: torch.Tensor, host_lens=None):
         """codes (8,N,T') int32/int64 cuda -> wav (N, 1280 T'), out lens."""
         nat = self._native_for(codes.device)
         _, N, Tc = codes.shape
@@ -354,9 +363,15 @@ class AudioCodec(nn.Module):
             n = min(mb, N - s)
             ws, nws = nat.workspace("detokenize", n, Tc)
             c_part = codes if N <= mb else codes[:, s:s + n].contiguous()
-            _lib.check(nat.lib.swc_detokenize(nat.handle, _ptr(c_part), int(codes.dtype == torch.int64), _ptr(lens[s:s + n]), n,
-                                              Tc, _ptr(wav[s:s + n]), _ptr(olens[s:s + n]), ws, nws, _stream()),
-                       "swc_detokenize")
+            if host_lens is not None and _RAGGED:
+                hl = (C.c_int64 * n)(*[int(v) for v in host_lens[s:s + n]])
+                _lib.check(nat.lib.swc_detokenize_ragged(nat.handle, _ptr(c_part), int(codes.dtype == torch.int64),
+                                                         _ptr(lens[s:s + n]), hl, n, Tc, _ptr(wav[s:s + n]),
+                                                         _ptr(olens[s:s + n]), ws, nws, _stream()), "swc_detokenize_ragged")
+            else:
+                _lib.check(nat.lib.swc_detokenize(nat.handle, _ptr(c_part), int(codes.dtype == torch.int64), _ptr(lens[s:s + n]), n,
+                                                  Tc, _ptr(wav[s:s + n]), _ptr(olens[s:s + n]), ws, nws, _stream()),
+                           "swc_detokenize")
         return wav, olens
 
     # ------------------------------------------------------------------ reference API
@@ -400,11 +415,15 @@ class AudioCodec(nn.Module):
             return torch.zeros((self.num_groups, 0, 375), dtype=torch.int32, device=device)
         width = max(j.n_valid for j in jobs)
         x = torch.zeros((len(jobs), width), dtype=torch.float32, device=device)
+        on_dev = {}                                   # every utterance crosses the bus once, windows are cut on the device
         for k, j in enumerate(jobs):
-            w = torch.as_tensor(wav_list[j.item])
-            x[k, : j.n_valid] = w[j.start:j.start + j.n_valid].to(device=device, dtype=torch.float32, non_blocking=True)
+            w = on_dev.get(j.item)
+            if w is None:
+                w = on_dev[j.item] = torch.as_tensor(wav_list[j.item]).reshape(-1).to(device=device, dtype=torch.float32,
+                                                                                      non_blocking=True)
+            x[k, : j.n_valid] = w[j.start:j.start + j.n_valid]
         wl = torch.tensor([j.n_valid for j in jobs], dtype=torch.int64).to(device, non_blocking=True)
-        return self._tokenize(x, wl, want_zq=False)[0]
+        return self._tokenize(x, wl, want_zq=False, host_lens=[j.n_valid for j in jobs])[0]
 
     def decode_jobs(self, codes_list, jobs, device) -> torch.Tensor:
         """Detokenize decode windows that share one pad length T' -> wav (len(jobs), 1280 T')."""
@@ -414,7 +433,7 @@ class AudioCodec(nn.Module):
             ct[:, k, : j.n_valid] = torch.as_tensor(codes_list[j.item])[:, j.start:j.start + j.n_valid].to(
                 device=device, dtype=torch.int64, non_blocking=True)
         cl = torch.tensor([j.n_valid for j in jobs], dtype=torch.int64).to(device, non_blocking=True)
-        return self._detokenize(ct, cl)[0]
+        return self._detokenize(ct, cl, host_lens=[j.n_valid for j in jobs])[0]
 
     @torch.inference_mode()
     def encode(self, wav_list, overlap_seconds=10, device=torch.device("cuda")):

@@ -321,6 +321,50 @@ int swc_detokenize(const swc_model* m, const void* codes, int codes_are_int64, c
   return stage_detokenize(c, codes, codes_are_int64, (const long long*)lens, batch, code_frames, wav, (long long*)out_lens);
 }
 
+// host-known lengths -> packed-token table (bf16 mode).  Returns false if the batch does not qualify (the callers then run
+// the padded path, which gives identical results).
+static bool build_ragged(RaggedTable& tab, const int64_t* host_lens, int batch, int mode /*0 samples -> tokens, 1 code frames -> tokens*/,
+                         int limit) {
+  if (!host_lens || batch <= 0 || batch > kMaxRagged) return false;
+  tab.nb = batch; tab.total = 0; tab.t_max = 0;
+  for (int b = 0; b < batch; ++b) {
+    long long l = host_lens[b] < 0 ? 0 : host_lens[b];
+    int tok;
+    if (mode == 0) {
+      if (l > limit) l = limit;                 // samples, clamped like mel_pad does
+      tok = (int)(((l + 159) / 160) / 2);      // mel_len // 2 (reference modules.py:322)
+    } else {
+      if (l > limit) l = limit;                 // code frames, clamped to the decode pad length T'
+      tok = (int)(4 * l);                       // up-sampler: len * 4 (reference modules.py:626)
+    }
+    tab.len[b] = tok;
+    tab.off[b] = tab.total;
+    tab.total += tok;
+    tab.t_max = tok > tab.t_max ? tok : tab.t_max;
+  }
+  tab.off[batch] = tab.total;
+  return tab.total > 0;
+}
+
+int swc_tokenize_ragged(const swc_model* m, const float* wav, int64_t wav_stride, int wav_cols, const int64_t* lengths,
+                        const int64_t* host_lengths, int batch, int32_t* codes, float* zq_cf, int64_t* codes_lens,
+                        void* workspace, size_t ws_bytes, void* stream) {
+  SWC_ENTER();
+  RaggedTable tab;
+  if (m->m.act_type() == 1 && build_ragged(tab, host_lengths, batch, 0, wav_cols < 480000 ? wav_cols : 480000)) c.rag = &tab;
+  return tokenize_chain(c, wav, wav_stride, wav_cols, (const long long*)lengths, batch, codes, zq_cf, (long long*)codes_lens);
+}
+
+int swc_detokenize_ragged(const swc_model* m, const void* codes, int codes_are_int64, const int64_t* lens,
+                          const int64_t* host_lens, int batch, int code_frames, float* wav, int64_t* out_lens, void* workspace,
+                          size_t ws_bytes, void* stream) {
+  SWC_ENTER();
+  SWC_REQUIRE(code_frames > 0, "detokenize: no code frames");
+  RaggedTable tab;
+  if (m->m.act_type() == 1 && build_ragged(tab, host_lens, batch, 1, code_frames)) c.rag = &tab;
+  return stage_detokenize(c, codes, codes_are_int64, (const long long*)lens, batch, code_frames, wav, (long long*)out_lens);
+}
+
 int swc_forward(const swc_model* m, const float* mel_cf, const int64_t* mel_lens, int batch, int mel_frames, float* wav,
                 int64_t* out_lens, int32_t* codes, void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();

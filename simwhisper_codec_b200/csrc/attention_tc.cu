@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <type_traits>
+
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
 
@@ -39,25 +41,36 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;                // log2 units
 
 struct AttnParams {
-  const long long* lens;
+  const long long* lens;   // device lengths (padded layout) or null
   bf16* out;
   int T, H, nb, n_qp, n_items;
 };
+// RAGGED: rows are packed (item b = rows [off[b], off[b] + len[b])), lengths come with the launch (no global load per
+// item), and rows >= len[b] do not exist: nothing is written for them.
+struct NoTable {};
 
 struct Item {
-  int b, h, q0, len, n_act, n_kt;
+  int b, h, q0, len, n_act, n_kt, row0;
   bool dead;
 };
-__device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
+template <typename TAB>
+__device__ __forceinline__ Item decode_item(const AttnParams& p, const TAB& tab, int item) {
   Item it;
   const int qp = item % p.n_qp;
   const int r = item / p.n_qp;
   it.h = r % p.H;
   it.b = r / p.H;
   it.q0 = qp * 2 * QT;
-  long long l = p.lens ? p.lens[it.b] : p.T;
-  it.len = (int)(l > p.T ? p.T : (l < 0 ? 0 : l));
+  if constexpr (std::is_same<TAB, RaggedTable>::value) {
+    it.len = tab.len[it.b];
+    it.row0 = tab.off[it.b];
+  } else {
+    long long l = p.lens ? p.lens[it.b] : p.T;
+    it.len = (int)(l > p.T ? p.T : (l < 0 ? 0 : l));
+    it.row0 = it.b * p.T;
+  }
   it.len = (int)uniform_u32((uint32_t)it.len);      // same address in every lane: tell the compiler it is warp-uniform
+  it.row0 = (int)uniform_u32((uint32_t)it.row0);
   it.dead = it.q0 >= it.len;
   it.n_act = (it.q0 + QT < it.len) ? 2 : 1;
   it.n_kt = (it.len + KT - 1) / KT;
@@ -90,9 +103,10 @@ __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]
   for (int c = 0; c < N / 32; ++c) tmem_st32(taddr + c * 32, *reinterpret_cast<const uint32_t(*)[32]>(&r[c * 32]));
 }
 
-template <int SPLIT>
+template <int SPLIT, typename TAB>
 __global__ void __launch_bounds__(96 + 256 * SPLIT, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, const __grid_constant__ TAB tab) {
+  constexpr bool kRagged = std::is_same<TAB, RaggedTable>::value;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
@@ -133,9 +147,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
       uint32_t q_cnt[2] = {0, 0};
       uint32_t kv_it = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const Item it = decode_item(p, item);
+        const Item it = decode_item(p, tab, item);
         if (it.dead) continue;
-        const int row0 = it.b * p.T;
+        const int row0 = it.row0;
         for (int i = 0; i < it.n_act; ++i) {
           const uint32_t qb = i * 2 + (q_cnt[i] & 1);
           mbar_wait(&q_empty[qb], ((q_cnt[i] >> 1) & 1) ^ 1);
@@ -174,7 +188,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
       };
       auto load_item = [&](Cursor& c) {            // position on the first non-dead item >= c.item
         for (; c.item < p.n_items; c.item += gridDim.x) {
-          const Item it = decode_item(p, c.item);
+          const Item it = decode_item(p, tab, c.item);
           if (it.dead) continue;
           c.n_kt = it.n_kt; c.active = i < it.n_act; c.j = 0;
           return;
@@ -263,11 +277,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
     float* xch = reinterpret_cast<float*>(smem + kXchOff) + i * (2 * SPLIT * QT);   // [2 buffers][SPLIT][128 rows]
     uint32_t s_cnt = 0, o_cnt = 0, x_cnt = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const Item it = decode_item(p, item);
+      const Item it = decode_item(p, tab, item);
       const int q = it.q0 + i * QT + row;
-      bf16* orow = p.out + ((long long)it.b * p.T + q) * DO + it.h * HD + part * ND;
-      if (it.dead || i >= it.n_act) {                 // tile of padded queries: defined zero output
-        if (q < p.T) {
+      bf16* orow = p.out + ((long long)it.row0 + q) * DO + it.h * HD + part * ND;
+      if (it.dead || i >= it.n_act) {                 // tile of padded queries: defined zero output (no such rows when packed)
+        if (!kRagged && q < p.T) {
 #pragma unroll
           for (int c = 0; c < ND / 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
         }
@@ -368,7 +382,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         for (int o2 = 0; o2 < SPLIT; ++o2) l += slot[o2 * QT + row];
       }
       const float inv = (q < it.len && l > 0.f) ? 1.0f / l : 0.f;     // padded query rows -> 0
-      if (q < p.T) {
+      if (kRagged ? q < it.len : q < p.T) {
 #pragma unroll
         for (int c = 0; c < ND / 8; ++c) {
           uint4 u;
@@ -393,11 +407,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
 
 }  // namespace
 
-int attention_tc(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, int num_sms, cudaStream_t s) {
+namespace {
+template <typename TAB>
+int attention_tc_launch(const bf16* qkv, bf16* out, const long long* lens, long long total_rows, int nb, int T, int H,
+                        const TAB& tab, int num_sms, cudaStream_t s) {
   SWC_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, "attention_tc: buffers must be 16-byte aligned");
   CUtensorMap tm;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)(3 * H * HD), (cuuint64_t)nb * T};
+    cuuint64_t dims[2] = {(cuuint64_t)(3 * H * HD), (cuuint64_t)total_rows};
     cuuint64_t strides[1] = {(cuuint64_t)(3 * H * HD) * 2};
     cuuint32_t box[2] = {HD, 128};
     SWC_TRY(make_tmap(&tm, 1, qkv, 2, dims, strides, box));
@@ -409,16 +426,26 @@ int attention_tc(const bf16* qkv, bf16* out, const long long* lens, int nb, int 
   static const int split = [] { const char* e = getenv("SWC_ATTN_SPLIT"); return (e && e[0] == '1') ? 1 : 2; }();
   static bool configured = false;
   if (!configured) {
-    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<1, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
   const int grid = std::min(p.n_items, num_sms);
   ProfScope ps(KC_ATTN, s);
-  if (split == 1) attention_tc_kernel<1><<<grid, 96 + 256, kSmemBytes, s>>>(tm, p);
-  else attention_tc_kernel<2><<<grid, 96 + 512, kSmemBytes, s>>>(tm, p);
+  if (split == 1) attention_tc_kernel<1, TAB><<<grid, 96 + 256, kSmemBytes, s>>>(tm, p, tab);
+  else attention_tc_kernel<2, TAB><<<grid, 96 + 512, kSmemBytes, s>>>(tm, p, tab);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+}  // namespace
+
+int attention_tc(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, int num_sms, cudaStream_t s) {
+  return attention_tc_launch(qkv, out, lens, (long long)nb * T, nb, T, H, NoTable{}, num_sms, s);
+}
+
+int attention_tc_ragged(const bf16* qkv, bf16* out, const RaggedTable& tab, int H, int num_sms, cudaStream_t s) {
+  SWC_REQUIRE(tab.nb > 0 && tab.nb <= kMaxRagged && tab.total > 0 && tab.t_max > 0, "attention_tc_ragged: bad table");
+  return attention_tc_launch(qkv, out, nullptr, (long long)tab.total, tab.nb, tab.t_max, H, tab, num_sms, s);
 }
 
 }  // namespace swc

@@ -1,6 +1,8 @@
 // Bandwidth-bound stages of the codec: LayerNorm, depthwise-conv+LayerNorm, anti-aliased Snake,
 // FSQ, layout conversion, log-mel pre/post passes, iSTFT overlap-add.  All are HBM-streaming
 // kernels: coalesced along the channel (contiguous) dimension, 16/32-byte vector accesses, fp32 math.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace swc {
@@ -551,6 +553,48 @@ int istft_ola(const float* frames, const float* win_sq, int nb, int T, float* wa
   dim3 grid(ceil_div(160 * T, 256), nb);
   ProfScope ps(KC_MISC, s);
   istft_ola_kernel<<<grid, 256, 0, s>>>(frames, win_sq, T, wav);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================
+// ragged pack / unpack of token rows (float4 / 8-byte granules; C is a multiple of 8)
+// ================================================================================================
+__global__ void pack_rows_kernel(const float* __restrict__ padded, float* __restrict__ packed, const __grid_constant__ RaggedTable tab,
+                                 int t_pad, int C4) {
+  const int b = blockIdx.y;
+  const int n = tab.len[b];
+  const float4* src = reinterpret_cast<const float4*>(padded) + (long long)b * t_pad * C4;
+  float4* dst = reinterpret_cast<float4*>(packed) + (long long)tab.off[b] * C4;
+  const long long total = (long long)n * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+template <typename T>
+__global__ void unpack_rows_kernel(const T* __restrict__ packed, T* __restrict__ padded, const __grid_constant__ RaggedTable tab,
+                                   int t_pad, int C8) {
+  // one uint4 = 8 bf16 or 4 fp32; C8 = uint4 per row
+  const int b = blockIdx.y;
+  const long long valid = (long long)tab.len[b] * C8, total = (long long)t_pad * C8;
+  const uint4* src = reinterpret_cast<const uint4*>(packed) + (long long)tab.off[b] * C8;
+  uint4* dst = reinterpret_cast<uint4*>(padded) + (long long)b * t_pad * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = i < valid ? src[i] : make_uint4(0, 0, 0, 0);
+}
+int pack_rows(const float* padded, float* packed, const RaggedTable& tab, int t_pad, int C, cudaStream_t s) {
+  SWC_REQUIRE(C % 4 == 0 && tab.nb > 0, "pack_rows: bad shape");
+  dim3 grid((unsigned)std::max(1, std::min(64, ceil_div(tab.t_max * (C / 4), 256))), tab.nb);
+  ProfScope ps(KC_MISC, s);
+  pack_rows_kernel<<<grid, 256, 0, s>>>(padded, packed, tab, t_pad, C / 4);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int unpack_rows(const void* packed, void* padded, int dtype, const RaggedTable& tab, int t_pad, int C, cudaStream_t s) {
+  SWC_REQUIRE(C % 8 == 0 && tab.nb > 0, "unpack_rows: bad shape");
+  const int c8 = dtype == 0 ? C / 4 : C / 8;
+  dim3 grid((unsigned)std::max(1, std::min(64, ceil_div(t_pad * c8, 256))), tab.nb);
+  ProfScope ps(KC_MISC, s);
+  if (dtype == 0) unpack_rows_kernel<float><<<grid, 256, 0, s>>>((const float*)packed, (float*)padded, tab, t_pad, c8);
+  else unpack_rows_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)packed, (bf16*)padded, tab, t_pad, c8);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -41,12 +41,28 @@ int mel_finalize(const float* logmel /*(nb,3000,80)*/, const float* item_max, in
 // iSTFT overlap-add ("same" padding): frames (nb,T,640) fp32 -> wav (nb,160T) fp32
 int istft_ola(const float* frames, const float* win_sq /*[640]*/, int nb, int T, float* wav, cudaStream_t s);
 
+// ---- ragged (packed valid tokens) transformer path: per-item token counts known on the host --------------------
+constexpr int kMaxRagged = 128;
+struct RaggedTable {          // passed by value to kernels (1 KB)
+  int nb = 0;
+  int t_max = 0;              // longest item
+  int total = 0;              // sum of len
+  int len[kMaxRagged];
+  int off[kMaxRagged + 1];    // off[b] = first packed row of item b
+};
+// packed[off[b] + t] = padded[b, t] for t < len[b]   (fp32 rows of C channels; padded has t_pad rows per item)
+int pack_rows(const float* padded, float* packed, const RaggedTable& tab, int t_pad, int C, cudaStream_t s);
+// padded[b, t] = t < len[b] ? packed[off[b] + t] : 0 for t < t_pad   (dtype 0 fp32 / 1 bf16)
+int unpack_rows(const void* packed, void* padded, int dtype, const RaggedTable& tab, int t_pad, int C, cudaStream_t s);
+
 // fp32 SIMT flash attention over fused qkv rows (nb*T, 3*H*64): q pre-scaled. Keys >= lens[b] masked.
 int attention_simt(const void* qkv, int type, void* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
 // bf16 tensor-core flash attention (mma.sync m16n8k16), same contract
 int attention_mma(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
 // bf16 flash attention on tcgen05 / TMEM / TMA (attention_tc.cu), same contract
 int attention_tc(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, int num_sms, cudaStream_t s);
+// the same kernel over packed rows: item b owns rows [off[b], off[b] + len[b]) of qkv / out; no padded rows exist
+int attention_tc_ragged(const bf16* qkv, bf16* out, const RaggedTable& tab, int H, int num_sms, cudaStream_t s);
 
 // misc
 int fill_f32(float* p, float v, long long n, cudaStream_t s);

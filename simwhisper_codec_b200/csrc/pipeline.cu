@@ -72,11 +72,15 @@ int run_attention(Ctx& c, const void* qkv, void* out, const long long* lens, int
 // Each sub-layer's output GEMM accumulates straight into the fp32 residual stream: h += out_proj(...) / h += fc2(...)
 // (bf16 mode: the epilogue's TMA store is a reduce-add performed by the L2; fp32 mode: the SIMT epilogue reads and
 // writes h in place).  LayerNorm then only reads h and writes the normalised operand of the next GEMM.
-int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const long long* lens, int nb, int T) {
+// With `rag` the rows of h are the packed valid tokens of all items (rag->total rows) and attention runs on the packed
+// layout; every other kernel is row-wise, so the result per token is bit-identical to the padded layout.
+int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const long long* lens, int nb, int T,
+                      const RaggedTable* rag) {
   const Model& m = *c.m;
   const int D = m.d_model, at = m.act_type();
   const int gelu = at == 1 ? 2 : 1;
-  const long long rows = (long long)nb * T;
+  const long long rows = rag ? (long long)rag->total : (long long)nb * T;
+  if (rag) { nb = 1; T = rag->total; }      // row-wise kernels see one long item
   const size_t mark = c.ws.mark();
   void* xn = c.ws.alloc(rows * D * esz(at));
   void* qkv = c.ws.alloc(rows * 3 * D * esz(at));
@@ -91,7 +95,8 @@ int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const
       set_out(d, qkv, 3 * D, 0);
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, at));
     }
-    SWC_TRY(run_attention(c, qkv, ao, lens, nb, T));
+    if (rag) SWC_TRY(attention_tc_ragged((const bf16*)qkv, (bf16*)ao, *rag, m.heads, m.num_sms, c.s));
+    else SWC_TRY(run_attention(c, qkv, ao, lens, nb, T));
     {
       GemmDesc d = base_desc(ao, D, 0, (int)rows, D, (int)rows, 1, L.out);
       set_out(d, h, D, 0);
@@ -147,8 +152,23 @@ int encoder_cl(Ctx& c, const void* mel_cl, const long long* enc_lens, int nb, in
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
     }
   }
-  SWC_TRY(transformer_stack(c, m.enc_layers, h, enc_lens, nb, T));
-  if (!c.dry) SWC_TRY(layernorm(h, nullptr, nullptr, enc_cl, at, m.enc_ln_g, m.enc_ln_b, 1e-5f, nb, T, T4, D, enc_lens, c.s));
+  const bool ragged = at == 1 && !c.force_simt && c.rag != nullptr && c.rag->nb == nb && c.rag->total > 0 && c.rag->t_max <= T;
+  float* hp = nullptr;
+  void* xnp = nullptr;
+  if (at == 1 && (c.dry || ragged)) {       // packed residual stream and packed normalised output
+    hp = (float*)c.ws.alloc((long long)nb * T * D * 4);
+    xnp = c.ws.alloc((long long)nb * T * D * esz(at));
+    SWC_TRY(c.ws.check());
+  }
+  if (ragged) {
+    SWC_TRY(pack_rows(h, hp, *c.rag, T, D, c.s));
+    SWC_TRY(transformer_stack(c, m.enc_layers, hp, nullptr, nb, T, c.rag));
+    SWC_TRY(layernorm(hp, nullptr, nullptr, xnp, at, m.enc_ln_g, m.enc_ln_b, 1e-5f, 1, c.rag->total, c.rag->total, D, nullptr, c.s));
+    SWC_TRY(unpack_rows(xnp, enc_cl, at, *c.rag, T4, D, c.s));      // rows >= len (and T..T4) are zero, as the masked LayerNorm writes them
+  } else {
+    SWC_TRY(transformer_stack(c, m.enc_layers, h, enc_lens, nb, T));
+    if (!c.dry) SWC_TRY(layernorm(h, nullptr, nullptr, enc_cl, at, m.enc_ln_g, m.enc_ln_b, 1e-5f, nb, T, T4, D, enc_lens, c.s));
+  }
   c.ws.release(mark);
   return 0;
 }
@@ -248,12 +268,30 @@ int decoder_cl(Ctx& c, float* h, const long long* lens, int nb, int T, void* mel
   const Model& m = *c.m;
   const int D = m.d_model, MP = m.mel_pitch, at = m.act_type();
   const size_t mark = c.ws.mark();
-  SWC_TRY(transformer_stack(c, m.dec_layers, h, lens, nb, T));
+  const bool ragged = at == 1 && !c.force_simt && c.rag != nullptr && c.rag->nb == nb && c.rag->total > 0 && c.rag->t_max <= T;
+  float* hp = nullptr;
+  void* xnp = nullptr;
+  if (at == 1 && (c.dry || ragged)) {
+    hp = (float*)c.ws.alloc((long long)nb * T * D * 4);
+    xnp = c.ws.alloc((long long)nb * T * D * esz(at));
+    SWC_TRY(c.ws.check());
+  }
+  if (ragged) {
+    SWC_TRY(pack_rows(h, hp, *c.rag, T, D, c.s));
+    SWC_TRY(transformer_stack(c, m.dec_layers, hp, nullptr, nb, T, c.rag));
+  } else {
+    SWC_TRY(transformer_stack(c, m.dec_layers, h, lens, nb, T));
+  }
   void* y = c.ws.alloc((long long)nb * T * D * esz(at));
   void* z = c.ws.alloc((long long)nb * 2 * T * D * esz(at));
   SWC_TRY(c.ws.check());
   if (!c.dry) {
-    SWC_TRY(layernorm(h, nullptr, nullptr, y, at, m.dec_ln_g, m.dec_ln_b, 1e-5f, nb, T, T, D, lens, c.s));
+    if (ragged) {
+      SWC_TRY(layernorm(hp, nullptr, nullptr, xnp, at, m.dec_ln_g, m.dec_ln_b, 1e-5f, 1, c.rag->total, c.rag->total, D, nullptr, c.s));
+      SWC_TRY(unpack_rows(xnp, y, at, *c.rag, T, D, c.s));
+    } else {
+      SWC_TRY(layernorm(h, nullptr, nullptr, y, at, m.dec_ln_g, m.dec_ln_b, 1e-5f, nb, T, T, D, lens, c.s));
+    }
     {   // deconv1 even output rows 2t: taps h[t-1] (k=2), h[t] (k=0)
       GemmDesc d = base_desc(y, D, (long long)T * D, T, D, T, nb, m.deconv1_even);
       d.n_taps = 2; d.tap_k = D;

@@ -33,9 +33,11 @@ struct Ctx {
   Arena ws;
   bool dry = false;          // size the workspace only, launch nothing
   bool force_simt = false;   // debugging: run bf16 operands through the SIMT kernels
+  const RaggedTable* rag = nullptr;   // bf16 mode: run the transformer stacks on packed valid tokens (host-known lengths)
 };
 
-int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const long long* lens, int nb, int T);
+int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const long long* lens, int nb, int T,
+                      const RaggedTable* rag = nullptr);
 int encoder_cl(Ctx& c, const void* mel_cl, const long long* enc_lens, int nb, int Tm, void* enc_cl);
 int downsample_fsq(Ctx& c, const void* enc_cl, const long long* code_lens, int nb, int T4, int* codes, float* zq_cf,
                    float* latent_cf, float* zq_cl);

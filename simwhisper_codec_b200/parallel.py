@@ -18,6 +18,8 @@ from . import windows
 def _gather_rows(local: torch.Tensor, counts: List[int], group) -> torch.Tensor:
     """all_gather of tensors (n_r, ...) with different n_r -> concatenation in rank order."""
     world = dist.get_world_size(group)
+    if world == 1:
+        return local
     nmax = max(counts) if counts else 0
     pad = torch.zeros((nmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local

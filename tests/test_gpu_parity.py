@@ -191,3 +191,22 @@ def test_bf16_full_window_properties(model16, model32, gen_params, sd_ex):
     assert s > 30.0
     y2 = small.inference_detokenize(r32["codes"], r32["codes_lengths"])
     assert torch.equal(y2["y"], y16["y"])
+
+
+def test_ragged_transformer_path_is_bit_identical(model16, monkeypatch):
+    """encode()/decode() know the window lengths on the host and run the bf16 transformer stacks on the packed valid tokens
+    only; every token must come out exactly as on the padded path."""
+    import simwhisper_codec_b200.audiocodec.model as mm
+    lens = [48123, 800000, 365000, 1280 * 250, 479999, 32000, 100, 161 * 3]
+    wavs = [synthetic_wave(6000 + i, n) for i, n in enumerate(lens)]
+    monkeypatch.setattr(mm, "_RAGGED", False)
+    c0 = model16.encode(wavs)["codes_list"]
+    w0 = model16.decode(c0)["syn_wav_list"]
+    monkeypatch.setattr(mm, "_RAGGED", True)
+    c1 = model16.encode(wavs)["codes_list"]
+    w1 = model16.decode(c0)["syn_wav_list"]
+    assert [tuple(c.shape) for c in c1] == [(8, n // 1280) for n in lens]
+    for a, b in zip(c0, c1):
+        assert torch.equal(a, b)
+    for a, b in zip(w0, w1):
+        assert torch.equal(a, b)
