@@ -117,15 +117,16 @@ __device__ __forceinline__ void store4(bf16* p, float4 v) {
 }
 
 template <typename TO, bool HAS_DELTA>
-__global__ void __launch_bounds__(kDwThreads) dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ delta,
-                                                                float* __restrict__ x_out, const float* __restrict__ w,
-                                                                const float* __restrict__ bias,
-                                                                const float* __restrict__ gamma,
-                                                                const float* __restrict__ beta, float eps,
-                                                                TO* __restrict__ out, int T, int strip) {
+__global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ delta,
+                                                                   float* __restrict__ x_out, const float* __restrict__ w,
+                                                                   const float* __restrict__ bias,
+                                                                   const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, float eps,
+                                                                   TO* __restrict__ out, int T, int strip) {
   constexpr int C = 512, R = kDwRows;
   __shared__ __align__(16) float red_sum[R][4];
   __shared__ __align__(16) float red_sq[R][4];
+  __shared__ __align__(16) float sw[7 * C];            // taps: read back per step instead of living in 28 registers
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c0 = tid * 4;
   const int b = blockIdx.y;
@@ -136,13 +137,11 @@ __global__ void __launch_bounds__(kDwThreads) dwconv7_ln_kernel(const float* __r
   float* xo = HAS_DELTA ? x_out + (long long)b * T * C + c0 : nullptr;
   TO* ob = out + (long long)b * T * C + c0;
 
-  float4 wk[7];
 #pragma unroll
-  for (int k = 0; k < 7; ++k) wk[k] = *reinterpret_cast<const float4*>(w + k * C + c0);
+  for (int k = 0; k < 7; ++k) *reinterpret_cast<float4*>(sw + k * C + c0) = *reinterpret_cast<const float4*>(w + k * C + c0);
   const float4 bs = *reinterpret_cast<const float4*>(bias + c0);
-  const float4 gm = *reinterpret_cast<const float4*>(gamma + c0);
-  const float4 bt = *reinterpret_cast<const float4*>(beta + c0);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // (each thread reads back only the taps it wrote: no barrier needed)
 
   // window[j] holds s(row base - 3 + j); rows outside [0, T) are the convolution's zero padding
   float4 win[R + 6];
@@ -158,9 +157,10 @@ __global__ void __launch_bounds__(kDwThreads) dwconv7_ln_kernel(const float* __r
 #pragma unroll
   for (int j = 0; j < 6; ++j) win[j] = load_row(t0 - 3 + j, j >= 3);
 
-  for (int base = t0; base < t_end; base += R) {
-    // rows base+3 .. base+10 (the last three of the strip's final step belong to the next strip)
-    float4 xv[R], dv[R];
+  // rows base+3 .. base+10 of the coming step (the last three of the strip's final step belong to the next strip);
+  // the loads of step n+1 are issued before the LayerNorm phase of step n so that their latency hides behind it
+  float4 xv[R], dv[R];
+  auto fetch = [&](int base) {
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int t = base + 3 + j;
@@ -168,6 +168,9 @@ __global__ void __launch_bounds__(kDwThreads) dwconv7_ln_kernel(const float* __r
       xv[j] = ok ? *reinterpret_cast<const float4*>(xb + (long long)t * C) : zero4;
       if (HAS_DELTA) dv[j] = ok ? *reinterpret_cast<const float4*>(db + (long long)t * C) : zero4;
     }
+  };
+  fetch(t0);
+  for (int base = t0; base < t_end; base += R) {
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int t = base + 3 + j;
@@ -182,13 +185,18 @@ __global__ void __launch_bounds__(kDwThreads) dwconv7_ln_kernel(const float* __r
     float4 y[R];
     float psum[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float4 a = bs;
+    for (int r = 0; r < R; ++r) y[r] = bs;
 #pragma unroll
-      for (int k = 0; k < 7; ++k) a = f4_fma(win[r + k], wk[k], a);
-      y[r] = a;
-      psum[r] = warp_sum((a.x + a.y) + (a.z + a.w));
+    for (int k = 0; k < 7; ++k) {
+      const float4 wk = *reinterpret_cast<const float4*>(sw + k * C + c0);
+#pragma unroll
+      for (int r = 0; r < R; ++r) y[r] = f4_fma(win[r + k], wk, y[r]);
     }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) win[j] = win[j + R];
+    if (base + R < t_end) fetch(base + R);
+#pragma unroll
+    for (int r = 0; r < R; ++r) psum[r] = warp_sum((y[r].x + y[r].y) + (y[r].z + y[r].w));
     if (lane == 0) {
 #pragma unroll
       for (int r = 0; r < R; ++r) red_sum[r][warp] = psum[r];
@@ -207,6 +215,8 @@ __global__ void __launch_bounds__(kDwThreads) dwconv7_ln_kernel(const float* __r
       for (int r = 0; r < R; ++r) red_sq[r][warp] = psum[r];
     }
     __syncthreads();
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + c0);
+    const float4 bt = *reinterpret_cast<const float4*>(beta + c0);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int t = base + r;
@@ -221,8 +231,6 @@ __global__ void __launch_bounds__(kDwThreads) dwconv7_ln_kernel(const float* __r
         store4(ob + (long long)t * C, o);
       }
     }
-#pragma unroll
-    for (int j = 0; j < 6; ++j) win[j] = win[j + R];
   }
 }
 
@@ -230,8 +238,8 @@ int dwconv7_ln(const float* x, const float* delta, float* x_out, const float* w7
                const float* beta, float eps, void* out, int out_type, int nb, int T, int C, cudaStream_t s) {
   SWC_REQUIRE(C == 512, "dwconv7_ln: only C=512 is built (got %d)", C);
   SWC_REQUIRE(!delta || (x_out && x_out != x), "dwconv7_ln: fused residual needs a distinct output stream buffer");
-  // strips of 128 rows (4.7 % halo re-reads) when that still gives every SM several blocks, else 32
-  const int strip = ((long long)nb * ceil_div(T, 128) >= 4 * 148) ? 128 : 32;
+  // strips of 64 rows (9 % halo re-reads, served by the L2) when that gives every SM many blocks, else 32
+  const int strip = ((long long)nb * ceil_div(T, 64) >= 16 * 148) ? 64 : 32;
   dim3 grid(ceil_div(T, strip), nb);
   ProfScope ps(KC_DWCONV_LN, s);
   if (out_type == 0) {
