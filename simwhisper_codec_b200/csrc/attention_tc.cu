@@ -14,6 +14,8 @@
 // Per tile and key block a softmax thread reads its 128 scores from TMEM, takes the row maximum, and only when the
 // maximum grew by more than 2^8 rescales its O row in TMEM (lazy rescale: the stale maximum is used otherwise, so
 // probabilities stay <= 256 and the final 1/l normalisation is exact); it then writes P as packed bf16 back to TMEM.
+// The normalised output tile is staged in shared memory and written as whole 128-byte rows (a thread-per-row store
+// touches 32 different lines per instruction).
 // TMEM columns: S0 0-127 | S1 128-255 | P0 256-319 | P1 320-383 | O0 384-447 | O1 448-511.
 #include <algorithm>
 #include <cstdlib>
@@ -29,13 +31,14 @@ namespace {
 
 using namespace ptx;
 
-constexpr int QT = 128, KT = 128, HD = 64, STAGES = 4;
+constexpr int QT = 128, KT = 128, HD = 64, STAGES = 3;
 constexpr int kTileBytes = 128 * 64 * 2;                 // 16 KB: Q, K or V tile
 constexpr int kQOff = 0, kKVOff = 4 * kTileBytes;      // Q: [tile][buffer]
 constexpr int kBarOff = kKVOff + STAGES * 2 * kTileBytes;
 constexpr int kNumBars = 4 + 4 + 2 * STAGES + 2 + 2 + 2 + 2 + 2;
 constexpr int kXchOff = kBarOff + kNumBars * 8 + 16;     // float [tile][buffer][part][row] exchange slots (SPLIT = 2)
-constexpr int kSmemBytes = kXchOff + 2 * 2 * 2 * QT * 4 + 1024;
+constexpr int kOutOff = (kXchOff + 2 * 2 * 2 * QT * 4 + 127) / 128 * 128;   // bf16 output tiles [tile][128 rows][128 B], XOR-swizzled
+constexpr int kSmemBytes = kOutOff + 2 * kTileBytes + 1024;
 constexpr uint32_t kColS = 0, kColP = 256, kColO = 384;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;                // log2 units
@@ -44,6 +47,7 @@ struct AttnParams {
   const long long* lens;   // device lengths (padded layout) or null
   bf16* out;
   int T, H, nb, n_qp, n_items;
+  long long* trace;        // optional per-phase clock64 stamps of CTA 0 (tools/attn_trace.py); null in normal runs
 };
 // RAGGED: rows are packed (item b = rows [off[b], off[b] + len[b])), lengths come with the launch (no global load per
 // item), and rows >= len[b] do not exist: nothing is written for them.
@@ -53,22 +57,28 @@ struct Item {
   int b, h, q0, len, n_act, n_kt, row0;
   bool dead;
 };
+// raw length of the item's sequence: the only memory access of the decode, split off so that it can be issued one item ahead
 template <typename TAB>
-__device__ __forceinline__ Item decode_item(const AttnParams& p, const TAB& tab, int item) {
+__device__ __forceinline__ int item_len_raw(const AttnParams& p, const TAB& tab, int item) {
+  const int b = item / (p.n_qp * p.H);
+  if constexpr (std::is_same<TAB, RaggedTable>::value) {
+    return tab.len[b];
+  } else {
+    long long l = p.lens ? p.lens[b] : p.T;
+    return (int)(l > p.T ? p.T : (l < 0 ? 0 : l));
+  }
+}
+template <typename TAB>
+__device__ __forceinline__ Item decode_item(const AttnParams& p, const TAB& tab, int item, int len_raw) {
   Item it;
   const int qp = item % p.n_qp;
   const int r = item / p.n_qp;
   it.h = r % p.H;
   it.b = r / p.H;
   it.q0 = qp * 2 * QT;
-  if constexpr (std::is_same<TAB, RaggedTable>::value) {
-    it.len = tab.len[it.b];
-    it.row0 = tab.off[it.b];
-  } else {
-    long long l = p.lens ? p.lens[it.b] : p.T;
-    it.len = (int)(l > p.T ? p.T : (l < 0 ? 0 : l));
-    it.row0 = it.b * p.T;
-  }
+  it.len = len_raw;
+  if constexpr (std::is_same<TAB, RaggedTable>::value) it.row0 = tab.off[it.b];
+  else it.row0 = it.b * p.T;
   it.len = (int)uniform_u32((uint32_t)it.len);      // same address in every lane: tell the compiler it is warp-uniform
   it.row0 = (int)uniform_u32((uint32_t)it.row0);
   it.dead = it.q0 >= it.len;
@@ -76,7 +86,15 @@ __device__ __forceinline__ Item decode_item(const AttnParams& p, const TAB& tab,
   it.n_kt = (it.len + KT - 1) / KT;
   return it;
 }
+template <typename TAB>
+__device__ __forceinline__ Item decode_item(const AttnParams& p, const TAB& tab, int item) {
+  return decode_item(p, tab, item, item_len_raw(p, tab, item));
+}
 
+__device__ __forceinline__ void trace_stamp(const AttnParams& p, int slot, int& idx) {
+  // slots: 0 softmax warp of tile 0, 1 issuer of tile 0, 2 TMA producer; 4096 stamps each
+  if (p.trace && blockIdx.x == 0 && idx < 4096) p.trace[slot * 4096 + idx++] = clock64();
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -276,8 +294,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
     const int DO = p.H * HD;
     float* xch = reinterpret_cast<float*>(smem + kXchOff) + i * (2 * SPLIT * QT);   // [2 buffers][SPLIT][128 rows]
     uint32_t s_cnt = 0, o_cnt = 0, x_cnt = 0;
+    int tr = 0;
+    const bool tracer = (warp == 3 && lane == 0);
+    uint8_t* ostage = smem + kOutOff + i * kTileBytes;
+    int len_next = blockIdx.x < p.n_items ? item_len_raw(p, tab, blockIdx.x) : 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const Item it = decode_item(p, tab, item);
+      const Item it = decode_item(p, tab, item, len_next);
+      if (item + (int)gridDim.x < p.n_items) len_next = item_len_raw(p, tab, item + gridDim.x);   // in flight during this item
       const int q = it.q0 + i * QT + row;
       bf16* orow = p.out + ((long long)it.row0 + q) * DO + it.h * HD + part * ND;
       if (it.dead || i >= it.n_act) {                 // tile of padded queries: defined zero output (no such rows when packed)
@@ -288,8 +311,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         continue;
       }
       float m_used = -INFINITY, l = 0.f;
+      if (tracer) trace_stamp(p, 0, tr);                 // A: item decoded
       for (int j = 0; j < it.n_kt; ++j) {
         mbar_wait(&s_full[i], s_cnt & 1);
+        if (tracer) trace_stamp(p, 0, tr);               // B: S ready
         ++s_cnt;
         tc_fence_after();
         uint32_t s[NC];
@@ -361,9 +386,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[i]);
+        if (tracer) trace_stamp(p, 0, tr);               // C: P handed over
       }
       // ---- final: O_i / l -> bf16 rows
       mbar_wait(&o_done[i], o_cnt & 1);
+      if (tracer) trace_stamp(p, 0, tr);                 // D: last P V done
       ++o_cnt;
       tc_fence_after();
       uint32_t o[ND];
@@ -382,17 +409,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         for (int o2 = 0; o2 < SPLIT; ++o2) l += slot[o2 * QT + row];
       }
       const float inv = (q < it.len && l > 0.f) ? 1.0f / l : 0.f;     // padded query rows -> 0
-      if (kRagged ? q < it.len : q < p.T) {
+      {
+        // this thread's ND dims of row `row` -> staging tile (16-byte chunk c of row r lives at chunk c ^ (r & 7))
+        const uint32_t srow = smem_u32(ostage) + (uint32_t)row * 128u;
 #pragma unroll
         for (int c = 0; c < ND / 8; ++c) {
-          uint4 u;
-          u.x = pack2(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
-          u.y = pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
-          u.z = pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
-          u.w = pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 8) = u;
+          const uint32_t chunk = (uint32_t)(part * (ND / 8) + c);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((chunk ^ (uint32_t)(row & 7)) << 4)),
+                       "r"(pack2(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv)),
+                       "r"(pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv)),
+                       "r"(pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv)),
+                       "r"(pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv))
+                       : "memory");
+        }
+        named_bar_sync(1 + i, 128 * SPLIT);
+        // whole 128-byte rows: each of the tile's 4*SPLIT warps writes 128 / (4*SPLIT) rows, 4 rows per instruction
+        constexpr int kRowsPerWarp = QT / (4 * SPLIT);
+        const int wt = sw % (4 * SPLIT);                 // warp index inside the tile
+        bf16* obase = p.out + ((long long)it.row0 + it.q0 + i * QT) * DO + it.h * HD;
+        const int row_limit = (kRagged ? it.len : p.T) - (it.q0 + i * QT);     // rows of this tile that exist
+#pragma unroll
+        for (int r4 = 0; r4 < kRowsPerWarp / 4; ++r4) {
+          const int r = wt * kRowsPerWarp + r4 * 4 + (lane >> 3), c = lane & 7;
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "r"(smem_u32(ostage) + (uint32_t)r * 128u + (((uint32_t)c ^ (uint32_t)(r & 7)) << 4)));
+          if (r < row_limit) *reinterpret_cast<uint4*>(obase + (long long)r * DO + c * 8) = v;
         }
       }
+      if (tracer) trace_stamp(p, 0, tr);                 // E: item stored
     }
   }
 
@@ -406,6 +451,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
 }
 
 }  // namespace
+
+long long* g_attn_trace = nullptr;   // set by swc_debug_attn_trace_enable
 
 namespace {
 template <typename TAB>
@@ -423,6 +470,7 @@ int attention_tc_launch(const bf16* qkv, bf16* out, const long long* lens, long 
   p.lens = lens; p.out = out; p.T = T; p.H = H; p.nb = nb;
   p.n_qp = ceil_div(T, 2 * QT);
   p.n_items = p.n_qp * H * nb;
+  p.trace = g_attn_trace;
   static const int split = [] { const char* e = getenv("SWC_ATTN_SPLIT"); return (e && e[0] == '1') ? 1 : 2; }();
   static bool configured = false;
   if (!configured) {
@@ -449,3 +497,19 @@ int attention_tc_ragged(const bf16* qkv, bf16* out, const RaggedTable& tab, int 
 }
 
 }  // namespace swc
+
+// ---- debug: per-phase clock stamps of CTA 0 (tools/attn_trace.py) ----------------------------------------------------
+extern "C" int swc_debug_attn_trace(int enable, long long* host_out, int n) {
+  using namespace swc;
+  if (enable) {
+    if (!g_attn_trace && cudaMalloc(&g_attn_trace, 3 * 4096 * sizeof(long long)) != cudaSuccess) return -1;
+    cudaMemset(g_attn_trace, 0, 3 * 4096 * sizeof(long long));
+    return 0;
+  }
+  if (!g_attn_trace) return -1;
+  cudaDeviceSynchronize();
+  if (host_out) cudaMemcpy(host_out, g_attn_trace, sizeof(long long) * (size_t)(n < 3 * 4096 ? n : 3 * 4096), cudaMemcpyDeviceToHost);
+  cudaFree(g_attn_trace);
+  g_attn_trace = nullptr;
+  return 0;
+}

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Phase timeline of one persistent CTA of the tcgen05 attention kernel (clock64 stamps of the first softmax warp of query
+tile 0): A item decoded | per key block: B S ready, C P handed over | D last P V done | E item stored."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from simwhisper_codec_b200 import _lib  # noqa: E402
+
+
+def main():
+    lib = _lib.load()
+    fn = lib.swc_debug_attn_trace
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_int]
+    B, T, H = 64, 1500, 12
+    g = torch.Generator(device="cuda").manual_seed(1)
+    qkv = torch.randn(B, T, 3 * H * 64, device="cuda", generator=g) * 0.7
+    qkv[..., : H * 64] *= 0.125
+    qkv = qkv.bfloat16()
+    lens = torch.full((B,), T, device="cuda", dtype=torch.int64)
+    out = torch.empty(B, T, H * 64, device="cuda", dtype=torch.bfloat16)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run():
+        _lib.check(lib.swc_test_attention(3, C.c_void_p(qkv.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(lens.data_ptr()),
+                                          B, T, H, st), "attention")
+    run()
+    torch.cuda.synchronize()
+    assert fn(1, None, 0) == 0
+    run()
+    buf = np.zeros(3 * 4096, dtype=np.int64)
+    assert fn(0, buf.ctypes.data, buf.size) == 0
+    t = buf[:4096]
+    t = t[t > 0]
+    n_kt = 12
+    per = 1 + 2 * n_kt + 2
+    items = len(t) // per
+    t = t[: items * per].reshape(items, per)
+    A, B_, C_, D, E = t[:, 0], t[:, 1:1 + 2 * n_kt:2], t[:, 2:2 + 2 * n_kt:2], t[:, -2], t[:, -1]
+    print(f"{items} items traced; cycles (median over items 2..):")
+    sl = slice(2, None)
+    print("  item period (A -> next A)      ", int(np.median(np.diff(A)[sl])))
+    print("  A -> B0 (first S ready)        ", int(np.median((B_[:, 0] - A)[sl])))
+    print("  B_j -> C_j (softmax of a block)", int(np.median((C_ - B_)[sl])))
+    print("  C_j -> B_j+1 (wait for next S) ", int(np.median((B_[:, 1:] - C_[:, :-1])[sl])))
+    print("  C_last -> D (last P V)         ", int(np.median((D - C_[:, -1])[sl])))
+    print("  D -> E (O read, normalise, store)", int(np.median((E - D)[sl])))
+    print("  E -> next A (decode next item) ", int(np.median((A[1:] - E[:-1])[sl])))
+    print("  per-block period B_j -> B_j+1  ", int(np.median(np.diff(B_, axis=1)[sl])))
+    print("  block periods of one item      ", np.diff(B_[3]).tolist())
+
+
+if __name__ == "__main__":
+    main()
