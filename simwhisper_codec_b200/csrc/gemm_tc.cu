@@ -386,6 +386,7 @@ int gemm_tc(const GemmDesc& d, int kind, int out_type, int num_sms, cudaStream_t
   switch (kind) {
     case EPI_STORE: return out_type == 0 ? launch_bn<EPI_STORE, float>(d, num_sms, s) : launch_bn<EPI_STORE, bf16>(d, num_sms, s);
     case EPI_FSQ: return launch_bn<EPI_FSQ, float>(d, num_sms, s);
+    case EPI_POWER: return launch_bn<EPI_POWER, float>(d, num_sms, s);
     case EPI_HEAD: return launch_bn<EPI_HEAD, float>(d, num_sms, s);
   }
   set_error("gemm_tc: unsupported epilogue kind %d", kind);

@@ -493,6 +493,27 @@ int mel_pad(const float* wav, long long wav_stride, int wav_cols, const long lon
   return 0;
 }
 
+__global__ void mel_frames_split_kernel(const float* __restrict__ padded, bf16* __restrict__ frames) {
+  // one block = one frame; thread n < 448 handles sample n of the frame
+  const int t = blockIdx.x, b = blockIdx.y, n = threadIdx.x;
+  float x = 0.f;
+  if (n < 400) x = padded[(long long)b * (kMelSamples + 2 * kMelPad) + (long long)t * 160 + n];
+  const bf16 a1 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(a1);
+  const bf16 a2 = __float2bfloat16_rn(r1);
+  const bf16 a3 = __float2bfloat16_rn(r1 - __bfloat162float(a2));
+  bf16* o = frames + ((long long)b * kMelFrames + t) * (3 * 448) + n;
+  o[0] = a1; o[448] = a2; o[896] = a3;
+}
+
+int mel_frames_split(const float* padded, int nb, bf16* frames, cudaStream_t s) {
+  dim3 grid(kMelFrames, nb);
+  ProfScope ps(KC_MISC, s);
+  mel_frames_split_kernel<<<grid, 448, 0, s>>>(padded, frames);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <typename TO>
 __global__ void mel_finalize_kernel(const float* __restrict__ logmel, const float* __restrict__ item_max,
                                     float* __restrict__ mel_cf, TO* __restrict__ mel_cl, int cl_pitch) {

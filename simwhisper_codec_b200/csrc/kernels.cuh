@@ -35,6 +35,9 @@ int cl_to_cf(const void* in, int in_type, float* out, int nb, int C, int T, long
 // log-mel helpers
 int mel_pad(const float* wav, long long wav_stride, int wav_cols, const long long* lens, int nb,
             float* padded /*(nb, 480400)*/, long long* mel_lens, float* item_max, cudaStream_t s);
+// framed + split signal for the tensor-core DFT: frames (nb, 3000, 3, 448) bf16 with x = a1 + a2 + a3 per sample
+// (columns 400..447 of every plane are zero); reads the reflect-padded signal written by mel_pad
+int mel_frames_split(const float* padded, int nb, bf16* frames, cudaStream_t s);
 int mel_finalize(const float* logmel /*(nb,3000,80)*/, const float* item_max, int nb, float* mel_cf,
                  void* mel_cl, int cl_type, int cl_pitch, cudaStream_t s);
 

@@ -71,6 +71,7 @@ struct Model {
   const float *voc_norm_g, *voc_norm_b, *voc_final_g, *voc_final_b;
   std::vector<VocosBlockW> voc_blocks;
   const float *w_dft, *w_melfb, *w_idft, *win_sq;
+  const void* w_dft6 = nullptr;    // [416][6*448] split operand (act dtype) for the tensor-core DFT
   const void* w_idft3 = nullptr;   // [n_fft][3*NP] split operand (act dtype) for the tensor-core iDFT
 
   int act_type() const { return precision; }   // 0 fp32, 1 bf16

@@ -330,6 +330,22 @@ int pack_model(Model& m) {
         o[(size_t)(2 * k) * NF + n] = (float)(win * std::cos(ang));
         o[(size_t)(2 * k + 1) * NF + n] = (float)(-win * std::sin(ang));
       }
+    // bf16 tensor-core form: w = w1 + w2 + w3 (three bf16 terms = 24 mantissa bits); rows hold the six products' W factors
+    // [w1 | w2 | w1 | w3 | w2 | w1] (each zero-padded 400 -> 448 columns) against the frame planes (a1,a1,a2,a1,a2,a3)
+    {
+      const int KT = 448;
+      auto& o6 = P.put("mel.dft.w6", (size_t)NROW * 6 * KT, true);
+      static const int which[6] = {0, 1, 0, 2, 1, 0};
+      for (int r = 0; r < NROW; ++r)
+        for (int n = 0; n < NF; ++n) {
+          const float w = o[(size_t)r * NF + n];
+          float part[3];
+          part[0] = bf16_round(w);
+          part[1] = bf16_round(w - part[0]);
+          part[2] = bf16_round(w - part[0] - part[1]);
+          for (int t = 0; t < 6; ++t) o6[(size_t)r * 6 * KT + (size_t)t * KT + n] = part[which[t]];
+        }
+    }
     auto& fb = P.put("mel.fb.w", (size_t)MB * KP, false);
     const double mlo = hz_to_mel(0.0), mhi = hz_to_mel(8000.0);
     std::vector<double> hz(MB + 2);
@@ -464,6 +480,7 @@ int upload_model(Model& m, int device) {
   m.w_idft = F("voc.idft.w"); m.win_sq = F("voc.win_sq");
   m.w_idft3 = m.tab.count("voc.idft.w3") ? m.tab["voc.idft.w3"].dev : nullptr;
   m.w_dft = F("mel.dft.w"); m.w_melfb = F("mel.fb.w");
+  m.w_dft6 = m.tab.count("mel.dft.w6") ? m.tab["mel.dft.w6"].dev : nullptr;
   m.uploaded = true;
   (void)g_slab_unused;
   return 0;

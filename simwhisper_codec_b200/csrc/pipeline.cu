@@ -404,10 +404,23 @@ int mel_frontend(Ctx& c, const float* wav, long long wav_stride, int wav_cols, c
   float* power = (float*)c.ws.alloc((long long)nb * 3000 * 208 * 4);
   float* logmel = (float*)c.ws.alloc((long long)nb * 3000 * 80 * 4);
   float* item_max = (float*)c.ws.alloc((long long)nb * 4);
+  const bool tc_dft = m.act_type() == 1 && !c.force_simt && m.w_dft6 != nullptr;
+  bf16* frames = (m.act_type() == 1) ? (bf16*)c.ws.alloc((long long)nb * 3000 * 3 * 448 * 2) : nullptr;
   SWC_TRY(c.ws.check());
   if (!c.dry) {
     SWC_TRY(mel_pad(wav, wav_stride, wav_cols, lens, nb, padded, mel_lens, item_max, c.s));
-    {   // frames are rows of the padded signal at stride 160; Hann window folded into the DFT operand
+    if (tc_dft) {
+      // windowed DFT on the tensor cores at fp32 accuracy: sample and operand are split into three bf16 terms and the six
+      // significant products a1w1 + a1w2 + a2w1 + a1w3 + a2w2 + a3w1 accumulate in fp32 (one 6-tap GEMM, K = 6 x 448)
+      SWC_TRY(mel_frames_split(padded, nb, frames, c.s));
+      LinearW w; w.w = m.w_dft6; w.bias = nullptr; w.N = 416; w.w_rows = 416; w.K = 448;
+      GemmDesc d = base_desc(frames, 3 * 448, (long long)3000 * 3 * 448, 3000, 3 * 448, 3000, nb, w);
+      d.n_taps = 6; d.tap_k = 448;
+      const int plane[6] = {0, 0, 1, 0, 1, 2};
+      for (int t = 0; t < 6; ++t) { d.tap_row[t] = 0; d.tap_col[t] = plane[t] * 448; }
+      set_out(d, power, 208, (long long)3000 * 208);
+      SWC_TRY(gemm_tc(d, EPI_POWER, 0, m.num_sms, c.s));
+    } else {   // frames are rows of the padded signal at stride 160; Hann window folded into the DFT operand
       LinearW w; w.w = m.w_dft; w.bias = nullptr; w.N = 416; w.w_rows = 416; w.K = 400;
       GemmDesc d = base_desc(padded, 160, 480400, 3000, 400, 3000, nb, w);
       set_out(d, power, 208, (long long)3000 * 208);

@@ -210,3 +210,23 @@ def test_ragged_transformer_path_is_bit_identical(model16, monkeypatch):
         assert torch.equal(a, b)
     for a, b in zip(w0, w1):
         assert torch.equal(a, b)
+
+
+def test_mel_bf16_mode_keeps_fp32_accuracy(model16):
+    """In bf16 mode the log-mel front end runs its DFT on the tensor cores as a six-product split-bf16 GEMM with fp32
+    accumulation; it must still meet the fp32 bound against the reference (mel max-abs-err <= 1e-4)."""
+    g = load_golden("api_10s_ex.npz")
+    w = synthetic_wave(1000, 160000).cuda()
+    mel, mel_lens = model16._mel(w[None, :], torch.tensor([160000], device="cuda"))
+    assert int(mel_lens[0]) == 1000
+    assert np.abs(mel[0, :, :1008].cpu().numpy() - g["mel"]).max() <= 1e-4
+    assert np.abs(mel[0, :, 1008:].cpu().numpy()[:, ::97] - g["mel_tail"]).max() <= 1e-4
+    # a high-dynamic-range signal (tone + faint noise, 80 dB apart): the small bins must not be swamped by the split's
+    # rounding.  Truth = the oracle in float64; the reference's own fp32 path is ~7e-5 away from it on such signals
+    # (SURVEY 7.2 item 5), so both device paths get the same 1e-4 budget against the truth.
+    t = torch.arange(480000) / 16000.0
+    x = 0.9 * torch.sin(2 * torch.pi * 440.0 * t) + 1e-4 * torch.randn(480000, generator=torch.Generator().manual_seed(3))
+    truth, _ = port.log_mel([x], dtype=torch.float64)
+    lens = torch.tensor([480000], device="cuda")
+    mel16, _ = model16._mel(x[None, :].cuda(), lens)
+    assert (mel16.cpu().double() - truth).abs().max().item() <= 1e-4
