@@ -36,8 +36,9 @@ GF_MEL = 1.061
 GF_IDFT = 2.465
 # DRAM traffic of the tcgen05 GEMM class per window, from the committed ncu launch list (profiles/r1_ncu_launches_v4.md)
 GEMM_DRAM_GB_PER_WINDOW = 2.30
-GF_TC_GEMM = GF_TOTAL - GF_ATTN - GF_MEL              # contractions that run on the tcgen05 GEMM kernels (the inverse DFT
-                                                       # included: it runs as a 3-product split-bf16 GEMM, counted once)
+GF_TC_GEMM = GF_TOTAL - GF_ATTN - 0.096              # contractions that run on the tcgen05 GEMM kernels: everything but
+                                                       # attention and the 80-bin mel filterbank (the forward and inverse DFTs
+                                                       # run as split-bf16 GEMMs; their algorithmic FLOPs are counted once)
 
 
 def gen_params():
@@ -120,8 +121,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="30 s windows per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--max-batch", type=int, default=int(os.environ.get("SWC_MAX_BATCH", 128)),
+    ap.add_argument("--max-batch", type=int, default=int(os.environ.get("SWC_MAX_BATCH", 256)),
                     help="windows per kernel launch (the 256-window step runs as 256/max_batch sub-batches)")
+    ap.add_argument("--e2e-chunk", type=int, default=128,
+                    help="windows per chunk of the end-to-end step (copies of one chunk overlap the compute of the other)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -179,10 +182,11 @@ def main():
         r = model.inference_tokenize(x_dev, lens)
         return model.inference_detokenize(r["codes"], r["codes_lengths"])
 
-    # end to end through the public API with HOST buffers: the batch goes through in `max_batch`-window chunks, each
+    # end to end through the public API with HOST buffers: the batch goes through in `e2e_chunk`-window chunks, each
     # chunk's host->device copy, compute and device->host copy on their own streams so copies overlap the other chunk's compute
     copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    chunks = [slice(s0, min(s0 + args.max_batch, B)) for s0 in range(0, B, args.max_batch)]
+    e2e_chunk = max(1, min(args.e2e_chunk, args.max_batch))
+    chunks = [slice(s0, min(s0 + e2e_chunk, B)) for s0 in range(0, B, e2e_chunk)]
 
     def step_e2e():
         main = torch.cuda.current_stream()
@@ -294,7 +298,7 @@ def main():
         "x_realtime_per_gpu": value / world,
         "e2e": {"value": e2e, "unit": "audio-s/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": host_x.numel() * 4, "d2h_bytes_per_step": host_y.numel() * 4 + host_codes.numel() * 4,
-                "api": "AudioCodec.inference_tokenize -> inference_detokenize per max_batch-window chunk from pinned host buffers; "
+                "api": "AudioCodec.inference_tokenize -> inference_detokenize per 128-window chunk from pinned host buffers; "
                        "H2D / compute / D2H of consecutive chunks overlap on three streams"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }

@@ -53,7 +53,6 @@ namespace {
 using namespace ptx;
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int kEpiWarps = 8, kThreads = 128 + 32 * kEpiWarps;
 
 struct Tc2Params {
   int m_rows, nb, N;
@@ -64,8 +63,10 @@ struct Tc2Params {
   const float* gamma;
 };
 
-template <int CG, int STAGES, int NBUF>
+template <int CG, int STAGES, int NBUF, int EW>
 struct Smem2 {
+  static constexpr int kEpiWarps = EW;                                  // 8 or 16: four TMEM lane groups x EW/4 column slices
+  static constexpr int kThreads = 128 + 32 * EW;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -118,11 +119,13 @@ __device__ __forceinline__ void epi4(const uint32_t* acc, const float* sb, const
   }
 }
 
-template <int CG, int STAGES, int NBUF, int ACT, bool GAMMA, bool REDUCE, typename TO>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CG, int STAGES, int NBUF, int EW, int ACT, bool GAMMA, bool REDUCE, typename TO>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmO, const Tc2Params p) {
-  using L = Smem2<CG, STAGES, NBUF>;
+  using L = Smem2<CG, STAGES, NBUF, EW>;
+  constexpr int kEpiWarps = EW;
+  constexpr int kSlice = BN / (EW / 4);          // accumulator columns per epilogue warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -219,7 +222,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp >= 4) {
     const int ew = warp - 4;
     const int lg = ew & 3;                    // TMEM lane group of this warp: lanes [32 lg, 32 lg + 32)
-    const int c_base = (ew >> 2) * (BN / 2);  // this warp's 128 accumulator columns
+    const int c_base = (ew >> 2) * kSlice;    // this warp's accumulator columns
     constexpr bool kF32 = sizeof(TO) == 4;
     uint8_t* stage_out = smem + L::kOutOff + ew * NBUF * L::kOutBytesPerWarp;
     const uint32_t tempty_leader[2] = {CG == 1 ? smem_u32(&tempty[0]) : mapa(smem_u32(&tempty[0]), 0),
@@ -238,10 +241,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t rr[2][32];
       tmem_ld32(taddr, rr[0]);
 #pragma unroll
-      for (int sub = 0; sub < 4; ++sub) {
+      for (int sub = 0; sub < kSlice / 32; ++sub) {
         tmem_ld_wait();
-        if (sub + 1 < 4) tmem_ld32(taddr + (sub + 1) * 32, rr[(sub + 1) & 1]);
-        if (sub == 3) {                       // accumulator fully in registers: hand the TMEM buffer back
+        if (sub + 1 < kSlice / 32) tmem_ld32(taddr + (sub + 1) * 32, rr[(sub + 1) & 1]);
+        if (sub == kSlice / 32 - 1) {                       // accumulator fully in registers: hand the TMEM buffer back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
@@ -303,9 +306,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int CG, int STAGES, int NBUF, int ACT, bool GAMMA, bool REDUCE, typename TO>
+template <int CG, int STAGES, int NBUF, int EW, int ACT, bool GAMMA, bool REDUCE, typename TO>
 int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
-  using L = Smem2<CG, STAGES, NBUF>;
+  using L = Smem2<CG, STAGES, NBUF, EW>;
   constexpr int out_type = sizeof(TO) == 4 ? 0 : 1;
   CUtensorMap tmA, tmW, tmO;
   {
@@ -337,7 +340,7 @@ int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
   p.n_taps = d.n_taps; p.kb_per_tap = d.tap_k / BK;
   for (int i = 0; i < d.n_taps; ++i) { p.tap_row[i] = d.tap_row[i]; p.tap_col[i] = d.tap_col[i]; }
   p.bias = d.epi.bias; p.gamma = d.epi.gamma;
-  auto kern = gemm_tc2_kernel<CG, STAGES, NBUF, ACT, GAMMA, REDUCE, TO>;
+  auto kern = gemm_tc2_kernel<CG, STAGES, NBUF, EW, ACT, GAMMA, REDUCE, TO>;
   static bool configured = false;
   if (!configured) {
     SWC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -347,7 +350,7 @@ int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
   const int grid = CG * (int)std::min<long long>(total, num_sms / CG);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(L::kThreads);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -359,23 +362,23 @@ int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
   return 0;
 }
 
-template <int CG, int STAGES, int NBUF>
+template <int CG, int STAGES, int NBUF, int EW>
 int dispatch2(const GemmDesc& d, int out_type, int num_sms, cudaStream_t s) {
   const int act = d.epi.act;
   const bool gamma = d.epi.gamma != nullptr;
   const bool reduce = d.epi.residual != nullptr;      // eligibility guarantees residual == out (fp32, same addressing)
   if (out_type == 0) {
     if (reduce) {
-      if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, 0, false, true, float>(d, num_sms, s);
-      if (act == 0 && gamma) return launch2<CG, STAGES, NBUF, 0, true, true, float>(d, num_sms, s);
+      if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, EW, 0, false, true, float>(d, num_sms, s);
+      if (act == 0 && gamma) return launch2<CG, STAGES, NBUF, EW, 0, true, true, float>(d, num_sms, s);
     } else {
-      if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, 0, false, false, float>(d, num_sms, s);
-      if (act == 0 && gamma) return launch2<CG, STAGES, NBUF, 0, true, false, float>(d, num_sms, s);
-      if (act == 2 && !gamma) return launch2<CG, STAGES, NBUF, 2, false, false, float>(d, num_sms, s);
+      if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, EW, 0, false, false, float>(d, num_sms, s);
+      if (act == 0 && gamma) return launch2<CG, STAGES, NBUF, EW, 0, true, false, float>(d, num_sms, s);
+      if (act == 2 && !gamma) return launch2<CG, STAGES, NBUF, EW, 2, false, false, float>(d, num_sms, s);
     }
   } else if (!reduce) {
-    if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, 0, false, false, bf16>(d, num_sms, s);
-    if (act == 2 && !gamma) return launch2<CG, STAGES, NBUF, 2, false, false, bf16>(d, num_sms, s);
+    if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, EW, 0, false, false, bf16>(d, num_sms, s);
+    if (act == 2 && !gamma) return launch2<CG, STAGES, NBUF, EW, 2, false, false, bf16>(d, num_sms, s);
   }
   set_error("gemm_tc2: unsupported epilogue (act %d, gamma %d, out type %d)", act, (int)gamma, out_type);
   return -1;
@@ -400,9 +403,9 @@ int gemm_tc2(const GemmDesc& d, int out_type, int num_sms, int variant, cudaStre
   SWC_REQUIRE(gemm_tc2_eligible(d), "gemm_tc2: problem not eligible (residual/out2/act/N)");
   SWC_REQUIRE(d.m_rows > 0 && d.nb > 0, "gemm_tc2: empty problem");
   SWC_REQUIRE(((uintptr_t)d.A & 15) == 0 && ((uintptr_t)d.W & 15) == 0, "gemm_tc2: operands must be 16-byte aligned");
-  if (variant == 1) return dispatch2<1, 4, 1>(d, out_type, num_sms, s);
-  if (variant == 3) return dispatch2<2, 5, 2>(d, out_type, num_sms, s);   // one stage fewer, double-buffered staging boxes
-  return dispatch2<2, 6, 1>(d, out_type, num_sms, s);                     // deepest operand ring that fits 227 KB
+  if (variant == 1) return dispatch2<1, 4, 1, 8>(d, out_type, num_sms, s);
+  if (variant == 3) return dispatch2<2, 5, 1, 16>(d, out_type, num_sms, s);  // 16 epilogue warps (64 columns each), 5-stage ring
+  return dispatch2<2, 6, 1, 8>(d, out_type, num_sms, s);                     // deepest operand ring that fits 227 KB
 }
 
 }  // namespace swc
