@@ -34,8 +34,8 @@ GF_TOTAL = 1311.86
 GF_ATTN = 24 * 6.912
 GF_MEL = 1.061
 GF_IDFT = 2.465
-# DRAM traffic of the tcgen05 GEMM class per window, from the committed ncu launch list (profiles/r1_ncu_launches_v4.md)
-GEMM_DRAM_GB_PER_WINDOW = 2.30
+# DRAM traffic of the tcgen05 GEMM class per window, from the committed ncu launch list (profiles/r1_ncu_launches_v6_final.md)
+GEMM_DRAM_GB_PER_WINDOW = 2.66
 GF_TC_GEMM = GF_TOTAL - GF_ATTN - 0.096              # contractions that run on the tcgen05 GEMM kernels: everything but
                                                        # attention and the 80-bin mel filterbank (the forward and inverse DFTs
                                                        # run as split-bf16 GEMMs; their algorithmic FLOPs are counted once)
@@ -189,8 +189,10 @@ def main():
     chunks = [slice(s0, min(s0 + e2e_chunk, B)) for s0 in range(0, B, e2e_chunk)]
 
     def step_e2e():
+        # Only event dependencies tie the three streams together, so consecutive steps pipeline as well: the next step's
+        # host->device copy runs under this step's compute, this step's device->host copy under the next step's compute
+        # (the caching allocator orders buffer reuse across streams through record_stream).
         main = torch.cuda.current_stream()
-        copy_in.wait_stream(main)
         staged = []
         for sl in chunks:
             with torch.cuda.stream(copy_in):
@@ -211,7 +213,6 @@ def main():
                 host_y[sl].copy_(out["y"][:, 0], non_blocking=True)
             r["codes"].record_stream(copy_out)
             out["y"].record_stream(copy_out)
-        main.wait_stream(copy_out)
 
     def barrier():
         torch.cuda.synchronize()
@@ -225,6 +226,8 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        main = torch.cuda.current_stream()
+        main.wait_stream(copy_out)          # the timed region ends when the last device->host copy has landed
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1) / steps
@@ -280,7 +283,7 @@ def main():
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                 "traffic": GEMM_DRAM_GB_PER_WINDOW * 1e9 * B / max(cls_n["gemm_tcgen05"], 1),
                 "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of the gemm_tc* launches of one "
-                                "step under ncu, profiles/r1_ncu_launches_v4.md, averaged per launch)",
+                                "step under ncu, profiles/r1_ncu_launches_v6_final.md, averaged per launch)",
                 "peak_source": peak_src,
                 "algorithmic_gflop_per_window": GF_TC_GEMM, "windows_per_step": B, "launches_per_step": cls_n["gemm_tcgen05"],
                 "avg_launch_ms": gemm_ms / max(cls_n["gemm_tcgen05"], 1),
