@@ -290,7 +290,7 @@ def main():
                 "class_ms_per_step": cls_ms, "class_share": {k: v / tot_cls for k, v in cls_ms.items()},
                 "class_launches": cls_n}
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
         v, dt = cpu_reference_run(1, 1)
         cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
                         "sample": "1 x 30 s window (tokenize+detokenize, fp32) after 1 warm-up, oracle/port.py, all host threads"}
