@@ -128,6 +128,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
+    # stdout carries exactly one JSON line: anything libraries print meanwhile (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -142,14 +152,14 @@ def main():
             return
         warm = min(args.warmup, 1)
         v, dt = cpu_reference_run(args.steps, warm)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "audio-sec/sec encode+decode (16 kHz)", "value": v, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": "1 x 30 s window per step (tokenize+detokenize), oracle/port.py on all host threads"},
             "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0})
         return
 
     import torch.distributed as dist
@@ -305,7 +315,7 @@ def main():
                        "H2D / compute / D2H of consecutive chunks overlap on three streams"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
