@@ -43,10 +43,17 @@ constexpr uint32_t kColS = 0, kColP = 256, kColO = 384;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;                // log2 units
 
+// n / d by one multiply-high (exact while n * d < 2^32): the per-item decode runs on every role's critical path
+struct FastDiv {
+  uint32_t mul, d;
+  __host__ void set(uint32_t dd) { d = dd; mul = (uint32_t)(((1ull << 32) + dd - 1) / dd); }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : __umulhi(n, mul); }
+};
 struct AttnParams {
   const long long* lens;   // device lengths (padded layout) or null
   bf16* out;
   int T, H, nb, n_qp, n_items;
+  FastDiv by_qp, by_h, by_qph;
   long long* trace;        // optional per-phase clock64 stamps of CTA 0 (tools/attn_trace.py); null in normal runs
 };
 // RAGGED: rows are packed (item b = rows [off[b], off[b] + len[b])), lengths come with the launch (no global load per
@@ -57,28 +64,33 @@ struct Item {
   int b, h, q0, len, n_act, n_kt, row0;
   bool dead;
 };
-// raw length of the item's sequence: the only memory access of the decode, split off so that it can be issued one item ahead
+// raw length of the item's sequence: the only memory access of the decode, split off so that it can be issued one item
+// ahead.  Nothing may depend on the loaded value before the next item starts (warps issue in order: a dependent
+// instruction right behind the load would stall for the whole L2 latency), so the clamp to [0, T] lives in decode_item.
 template <typename TAB>
-__device__ __forceinline__ int item_len_raw(const AttnParams& p, const TAB& tab, int item) {
-  const int b = item / (p.n_qp * p.H);
+__device__ __forceinline__ long long item_len_raw(const AttnParams& p, const TAB& tab, int item) {
+  const int b = (int)p.by_qph.div((uint32_t)item);
   if constexpr (std::is_same<TAB, RaggedTable>::value) {
     return tab.len[b];
   } else {
-    long long l = p.lens ? p.lens[b] : p.T;
-    return (int)(l > p.T ? p.T : (l < 0 ? 0 : l));
+    return p.lens ? p.lens[b] : (long long)p.T;
   }
 }
 template <typename TAB>
-__device__ __forceinline__ Item decode_item(const AttnParams& p, const TAB& tab, int item, int len_raw) {
+__device__ __forceinline__ Item decode_item(const AttnParams& p, const TAB& tab, int item, long long len_raw) {
   Item it;
-  const int qp = item % p.n_qp;
-  const int r = item / p.n_qp;
-  it.h = r % p.H;
-  it.b = r / p.H;
+  const int r = (int)p.by_qp.div((uint32_t)item);
+  const int qp = item - r * p.n_qp;
+  it.b = (int)p.by_h.div((uint32_t)r);
+  it.h = r - it.b * p.H;
   it.q0 = qp * 2 * QT;
-  it.len = len_raw;
-  if constexpr (std::is_same<TAB, RaggedTable>::value) it.row0 = tab.off[it.b];
-  else it.row0 = it.b * p.T;
+  if constexpr (std::is_same<TAB, RaggedTable>::value) {
+    it.len = (int)len_raw;
+    it.row0 = tab.off[it.b];
+  } else {
+    it.len = (int)(len_raw > p.T ? p.T : (len_raw < 0 ? 0 : len_raw));
+    it.row0 = it.b * p.T;
+  }
   it.len = (int)uniform_u32((uint32_t)it.len);      // same address in every lane: tell the compiler it is warp-uniform
   it.row0 = (int)uniform_u32((uint32_t)it.row0);
   it.dead = it.q0 >= it.len;
@@ -289,6 +301,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
     const int i = sw / (4 * SPLIT);                   // query tile
     const int part = (sw >> 2) % SPLIT;               // column part of the row
     const int lg = warp & 3;                          // TMEM lane group this warp may access
+    // the SPLIT warps that share a row group exchange maxima / sums through a barrier of their own (they sit on the same
+    // scheduler); only the output staging needs the whole tile (barrier 9 + i)
+    const int pair_bar = 1 + i * 4 + lg;
     const int row = lg * 32 + lane;                   // query row inside the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
     const int DO = p.H * HD;
@@ -297,7 +312,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
     int tr = 0;
     const bool tracer = (warp == 3 && lane == 0);
     uint8_t* ostage = smem + kOutOff + i * kTileBytes;
-    int len_next = blockIdx.x < p.n_items ? item_len_raw(p, tab, blockIdx.x) : 0;
+    long long len_next = blockIdx.x < p.n_items ? item_len_raw(p, tab, blockIdx.x) : 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const Item it = decode_item(p, tab, item, len_next);
       if (item + (int)gridDim.x < p.n_items) len_next = item_len_raw(p, tab, item + gridDim.x);   // in flight during this item
@@ -324,6 +339,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           for (int c = 0; c < NC / 32; ++c) tmem_ld32(sa + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
           tmem_ld_wait();
         }
+#ifdef SWC_ATTN_FINE_TRACE
+        if (tracer) trace_stamp(p, 0, tr);               // B1: S in registers
+#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[i]);
@@ -343,15 +361,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           float* slot = xch + (x_cnt & 1) * (SPLIT * QT);
           ++x_cnt;
           slot[part * QT + row] = mxl;
-          named_bar_sync(1 + i, 128 * SPLIT);
+          named_bar_sync(pair_bar, 32 * SPLIT);
 #pragma unroll
           for (int o = 0; o < SPLIT; ++o) mxl = fmaxf(mxl, slot[o * QT + row]);
         }
+#ifdef SWC_ATTN_FINE_TRACE
+        if (tracer) trace_stamp(p, 0, tr);               // B2: row maximum known
+#endif
         float scale = 1.0f;
         const bool grow = mxl > m_used + kRescaleThreshold;     // always true for j == 0 (m_used = -inf)
         if (grow) { scale = ex2(m_used - mxl); m_used = mxl; }   // j == 0: scale = 0, l = 0, O not yet written
-        float sum[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[NC / 2];
+        float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < NC; c += 4) {
           const float p0 = ex2(fmaf(__uint_as_float(s[c]), kLog2e, -m_used));
@@ -362,7 +383,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           pk[c >> 1] = pack2(p0, p1);
           pk[(c >> 1) + 1] = pack2(p2, p3);
         }
-        l = fmaf(l, scale, (sum[0] + sum[1]) + (sum[2] + sum[3]));   // this part's share of the row sum
+        const float bsum = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+        l = fmaf(l, scale, bsum);                       // this part's share of the row sum
+#ifdef SWC_ATTN_FINE_TRACE
+        if (tracer) trace_stamp(p, 0, tr);               // B3: exponentials done
+#endif
         if (j > 0) {
           mbar_wait(&o_done[i], o_cnt & 1);             // P_i(j-1) V accumulated: P_i is free, O_i is stable
           ++o_cnt;
@@ -377,6 +402,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
             tmem_st_n<ND>(oa, o);
           }
         }
+#ifdef SWC_ATTN_FINE_TRACE
+        if (tracer) trace_stamp(p, 0, tr);               // B4: previous P V done (P slot free)
+#endif
         {
           const uint32_t pa = lane_addr + kColP + i * 64 + part * (NC / 2);
 #pragma unroll
@@ -403,7 +431,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         float* slot = xch + (x_cnt & 1) * (SPLIT * QT);
         ++x_cnt;
         slot[part * QT + row] = l;
-        named_bar_sync(1 + i, 128 * SPLIT);
+        named_bar_sync(pair_bar, 32 * SPLIT);
         l = 0.f;
 #pragma unroll
         for (int o2 = 0; o2 < SPLIT; ++o2) l += slot[o2 * QT + row];
@@ -422,7 +450,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
                        "r"(pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv))
                        : "memory");
         }
-        named_bar_sync(1 + i, 128 * SPLIT);
+        named_bar_sync(9 + i, 128 * SPLIT);
         // whole 128-byte rows: each of the tile's 4*SPLIT warps writes 128 / (4*SPLIT) rows, 4 rows per instruction
         constexpr int kRowsPerWarp = QT / (4 * SPLIT);
         const int wt = sw % (4 * SPLIT);                 // warp index inside the tile
@@ -470,18 +498,23 @@ int attention_tc_launch(const bf16* qkv, bf16* out, const long long* lens, long 
   p.lens = lens; p.out = out; p.T = T; p.H = H; p.nb = nb;
   p.n_qp = ceil_div(T, 2 * QT);
   p.n_items = p.n_qp * H * nb;
+  SWC_REQUIRE((long long)p.n_items * std::max(p.n_qp * H, 1) < (1ll << 32), "attention_tc: too many work items (%d)", p.n_items);
+  p.by_qp.set((uint32_t)p.n_qp); p.by_h.set((uint32_t)H); p.by_qph.set((uint32_t)(p.n_qp * H));
   p.trace = g_attn_trace;
   static const int split = [] { const char* e = getenv("SWC_ATTN_SPLIT"); return (e && e[0] == '1') ? 1 : 2; }();
-  static bool configured = false;
-  if (!configured) {
-    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<1, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
-  }
   const int grid = std::min(p.n_items, num_sms);
   ProfScope ps(KC_ATTN, s);
-  if (split == 1) attention_tc_kernel<1, TAB><<<grid, 96 + 256, kSmemBytes, s>>>(tm, p, tab);
-  else attention_tc_kernel<2, TAB><<<grid, 96 + 512, kSmemBytes, s>>>(tm, p, tab);
+  auto go = [&](auto kern, int threads) -> int {
+    static bool configured = false;                  // one flag per instantiation (the lambda body is instantiated per kernel)
+    if (!configured) {
+      SWC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      configured = true;
+    }
+    kern<<<grid, threads, kSmemBytes, s>>>(tm, p, tab);
+    return 0;
+  };
+  const int rc = split == 1 ? go(attention_tc_kernel<1, TAB>, 96 + 256) : go(attention_tc_kernel<2, TAB>, 96 + 512);
+  if (rc) return rc;
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

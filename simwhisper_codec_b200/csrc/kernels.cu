@@ -261,17 +261,16 @@ int dwconv7_ln(const float* x, const float* delta, float* x_out, const float* w7
 //   y[t]    = sum_{k<12} v[cl2(2t+k-5)] f[k]
 // one thread = one channel, walking TCH consecutive frames with a 12-deep sliding window of v.
 // ================================================================================================
-constexpr int kSnakeChunk = 32;
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(128) aa_snake_kernel(const TI* __restrict__ in, TO* __restrict__ out,
                                                        const float* __restrict__ taps_up,
                                                        const float* __restrict__ taps_dn,
                                                        const float* __restrict__ alpha_log,
-                                                       const float* __restrict__ beta_log, int T, int C) {
+                                                       const float* __restrict__ beta_log, int T, int C, int chunk) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.z;
-  const int t0 = blockIdx.y * kSnakeChunk;
+  const int t0 = blockIdx.y * chunk;
   if (c >= C) return;
   float f[12], fd[12];
 #pragma unroll
@@ -282,18 +281,7 @@ __global__ void __launch_bounds__(128) aa_snake_kernel(const TI* __restrict__ in
   TO* y = out + (long long)b * T * C + c;
   const int T2 = 2 * T;
 
-  auto calc_v = [&](int m) -> float {
-    m = min(max(m, 0), T2 - 1);
-    const int q = m >> 1, odd = m & 1;
-    float acc = 0.f;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      int j = min(max(q - 3 + odd + a, 0), T - 1);
-      float xv = to_f32<TI>(x[(long long)j * C]);
-      float tap = odd ? f[10 - 2 * a] : f[11 - 2 * a];
-      acc = fmaf(xv, tap, acc);
-    }
-    const float u = 2.0f * acc;
+  auto snake = [&](float u) -> float {
     float sn;
     if constexpr (sizeof(TO) == 2) {
       // bf16 output: two-constant Cody-Waite reduction to [-pi, pi] + MUFU.SIN (abs error ~2^-21, far below bf16 rounding)
@@ -306,32 +294,65 @@ __global__ void __launch_bounds__(128) aa_snake_kernel(const TI* __restrict__ in
     }
     return u + inv_b * (sn * sn);
   };
+  auto calc_v = [&](int m) -> float {
+    m = min(max(m, 0), T2 - 1);
+    const int q = m >> 1, odd = m & 1;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      int j = min(max(q - 3 + odd + a, 0), T - 1);
+      float xv = to_f32<TI>(x[(long long)j * C]);
+      float tap = odd ? f[10 - 2 * a] : f[11 - 2 * a];
+      acc = fmaf(xv, tap, acc);
+    }
+    return snake(2.0f * acc);
+  };
 
   float vw[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) vw[k] = calc_v(2 * t0 + k - 5);
-  const int t1 = min(t0 + kSnakeChunk, T);
+  const int t1 = min(t0 + chunk, T);
+  // The two new window entries of a step, v[2s+5] (odd) and v[2s+6] (even) with s = t + 1, read the same six inputs
+  // x[cl(s) .. cl(s+5)]: a six-deep register window of x slides one frame per step (one load per frame instead of 12;
+  // same taps in the same order as calc_v, so the result is bit-identical).
+  float xs[6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) xs[a] = to_f32<TI>(x[(long long)min(t0 + 1 + a, T - 1) * C]);
   for (int t = t0; t < t1; ++t) {
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc = fmaf(vw[k], fd[k], acc);
     y[(long long)t * C] = from_f32<TO>(acc);
     if (t + 1 < t1) {
+      const float x_next = to_f32<TI>(x[(long long)min(t + 7, T - 1) * C]);     // x[cl(s + 6)], for the next step
 #pragma unroll
       for (int k = 0; k < 10; ++k) vw[k] = vw[k + 2];
-      vw[10] = calc_v(2 * (t + 1) + 5);
-      vw[11] = calc_v(2 * (t + 1) + 6);
+      const int s = t + 1;
+      float ao = 0.f, ae = 0.f;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        ao = fmaf(xs[a], f[10 - 2 * a], ao);
+        ae = fmaf(xs[a], f[11 - 2 * a], ae);
+      }
+      // positions past the end replicate v[2T-1] (the newest valid entry is then already in the window)
+      vw[10] = (2 * s + 5 <= T2 - 1) ? snake(2.0f * ao) : vw[9];
+      vw[11] = (2 * s + 6 <= T2 - 1) ? snake(2.0f * ae) : vw[10];
+#pragma unroll
+      for (int a = 0; a < 5; ++a) xs[a] = xs[a + 1];
+      xs[5] = x_next;
     }
   }
 }
 
 int aa_snake(const void* in, int in_type, void* out, int out_type, const float* taps_up, const float* taps_dn,
              const float* alpha_log, const float* beta_log, int nb, int T, int C, cudaStream_t s) {
-  dim3 grid(ceil_div(C, 128), ceil_div(T, kSnakeChunk), nb);
+  // frames per thread: the 12-entry window fill costs as much as six frames, so 64-frame chunks when the grid stays large
+  const int chunk = ((long long)nb * ceil_div(T, 64) * ceil_div(C, 128) >= 16 * 148) ? 64 : 32;
+  dim3 grid(ceil_div(C, 128), ceil_div(T, chunk), nb);
   ProfScope ps(KC_SNAKE, s);
-  if (in_type == 0 && out_type == 0) aa_snake_kernel<float, float><<<grid, 128, 0, s>>>((const float*)in, (float*)out, taps_up, taps_dn, alpha_log, beta_log, T, C);
-  else if (in_type == 0 && out_type == 1) aa_snake_kernel<float, bf16><<<grid, 128, 0, s>>>((const float*)in, (bf16*)out, taps_up, taps_dn, alpha_log, beta_log, T, C);
-  else if (in_type == 1 && out_type == 1) aa_snake_kernel<bf16, bf16><<<grid, 128, 0, s>>>((const bf16*)in, (bf16*)out, taps_up, taps_dn, alpha_log, beta_log, T, C);
+  if (in_type == 0 && out_type == 0) aa_snake_kernel<float, float><<<grid, 128, 0, s>>>((const float*)in, (float*)out, taps_up, taps_dn, alpha_log, beta_log, T, C, chunk);
+  else if (in_type == 0 && out_type == 1) aa_snake_kernel<float, bf16><<<grid, 128, 0, s>>>((const float*)in, (bf16*)out, taps_up, taps_dn, alpha_log, beta_log, T, C, chunk);
+  else if (in_type == 1 && out_type == 1) aa_snake_kernel<bf16, bf16><<<grid, 128, 0, s>>>((const bf16*)in, (bf16*)out, taps_up, taps_dn, alpha_log, beta_log, T, C, chunk);
   else { set_error("aa_snake: unsupported types %d->%d", in_type, out_type); return -1; }
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;

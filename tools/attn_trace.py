@@ -38,21 +38,28 @@ def main():
     t = buf[:4096]
     t = t[t > 0]
     n_kt = 12
-    per = 1 + 2 * n_kt + 2
+    per = 1 + 6 * n_kt + 2
     items = len(t) // per
     t = t[: items * per].reshape(items, per)
-    A, B_, C_, D, E = t[:, 0], t[:, 1:1 + 2 * n_kt:2], t[:, 2:2 + 2 * n_kt:2], t[:, -2], t[:, -1]
+    A, D, E = t[:, 0], t[:, -2], t[:, -1]
+    blk = t[:, 1:1 + 6 * n_kt].reshape(items, n_kt, 6)     # B, B1, B2, B3, B4, C per key block
+    B_, C_ = blk[:, :, 0], blk[:, :, 5]
     print(f"{items} items traced; cycles (median over items 2..):")
     sl = slice(2, None)
-    print("  item period (A -> next A)      ", int(np.median(np.diff(A)[sl])))
-    print("  A -> B0 (first S ready)        ", int(np.median((B_[:, 0] - A)[sl])))
-    print("  B_j -> C_j (softmax of a block)", int(np.median((C_ - B_)[sl])))
-    print("  C_j -> B_j+1 (wait for next S) ", int(np.median((B_[:, 1:] - C_[:, :-1])[sl])))
-    print("  C_last -> D (last P V)         ", int(np.median((D - C_[:, -1])[sl])))
-    print("  D -> E (O read, normalise, store)", int(np.median((E - D)[sl])))
-    print("  E -> next A (decode next item) ", int(np.median((A[1:] - E[:-1])[sl])))
-    print("  per-block period B_j -> B_j+1  ", int(np.median(np.diff(B_, axis=1)[sl])))
-    print("  block periods of one item      ", np.diff(B_[3]).tolist())
+    med = lambda a: int(np.median(a[sl]))
+    print("  item period (A -> next A)        ", med(np.diff(A)))
+    print("  A -> B0 (first S ready)          ", med(B_[:, 0] - A))
+    print("  B -> B1 (S: TMEM -> registers)   ", med(blk[:, :, 1] - blk[:, :, 0]))
+    print("  B1 -> B2 (row max + exchange)    ", med(blk[:, :, 2] - blk[:, :, 1]))
+    print("  B2 -> B3 (exponentials)          ", med(blk[:, :, 3] - blk[:, :, 2]))
+    print("  B3 -> B4 (wait previous P V)     ", med(blk[:, 1:, 4] - blk[:, 1:, 3]))
+    print("  B4 -> C (P -> TMEM, hand over)   ", med(blk[:, :, 5] - blk[:, :, 4]))
+    print("  C_j -> B_j+1 (wait for next S)   ", med(B_[:, 1:] - C_[:, :-1]))
+    print("  C_last -> D (last P V)           ", med(D - C_[:, -1]))
+    print("  D -> E (O read, normalise, store)", med(E - D))
+    print("  E -> next A (decode next item)   ", med(A[1:] - E[:-1]))
+    print("  per-block period B_j -> B_j+1    ", med(np.diff(B_, axis=1)))
+    print("  block periods of one item        ", np.diff(B_[3]).tolist())
 
 
 if __name__ == "__main__":
