@@ -116,6 +116,34 @@ __device__ __forceinline__ void store4(bf16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// Sums of 8 per-lane values over the warp in 9 shuffles instead of 40: each exchange halves the number of values a lane
+// carries (lane bit 4 / 3 / 2 picks which half it keeps), so after three exchanges a lane owns one row, and two more
+// exchanges finish that row.  Lane l ends with the total of row l >> 2; the lane pairs and their order are those of
+// warp_sum, so every total is bit-identical to it.
+__device__ __forceinline__ float warp_sum8(const float (&v)[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float a[4], b[2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float recv = __shfl_xor_sync(0xffffffffu, b4 ? v[k] : v[k + 4], 16);
+    a[k] = (b4 ? v[k + 4] : v[k]) + recv;
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float recv = __shfl_xor_sync(0xffffffffu, b3 ? a[k] : a[k + 2], 8);
+    b[k] = (b3 ? a[k + 2] : a[k]) + recv;
+  }
+  float c = (b2 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, b2 ? b[0] : b[1], 4);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;
+}
+template <typename TO>
+__device__ __forceinline__ float dw_rstd(float var_eps) {
+  if constexpr (sizeof(TO) == 2) return rsqrtf(var_eps);      // bf16 output: MUFU.RSQ (1 ulp) instead of sqrt + divide
+  else return 1.0f / sqrtf(var_eps);
+}
+
 template <typename TO, bool HAS_DELTA>
 __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ delta,
                                                                    float* __restrict__ x_out, const float* __restrict__ w,
@@ -196,10 +224,10 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
     for (int j = 0; j < 6; ++j) win[j] = win[j + R];
     if (base + R < t_end) fetch(base + R);
 #pragma unroll
-    for (int r = 0; r < R; ++r) psum[r] = warp_sum((y[r].x + y[r].y) + (y[r].z + y[r].w));
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) red_sum[r][warp] = psum[r];
+    for (int r = 0; r < R; ++r) psum[r] = (y[r].x + y[r].y) + (y[r].z + y[r].w);
+    {
+      const float tot = warp_sum8(psum, lane);          // lane l: row l >> 2
+      if ((lane & 3) == 0) red_sum[lane >> 2][warp] = tot;
     }
     __syncthreads();
     float mean[R];
@@ -208,11 +236,11 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
       const float4 p = *reinterpret_cast<const float4*>(red_sum[r]);
       mean[r] = ((p.x + p.y) + (p.z + p.w)) * (1.0f / C);
       const float dx = y[r].x - mean[r], dy = y[r].y - mean[r], dz = y[r].z - mean[r], dw = y[r].w - mean[r];
-      psum[r] = warp_sum(fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw));
+      psum[r] = fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw);
     }
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) red_sq[r][warp] = psum[r];
+    {
+      const float tot = warp_sum8(psum, lane);
+      if ((lane & 3) == 0) red_sq[lane >> 2][warp] = tot;
     }
     __syncthreads();
     const float4 gm = *reinterpret_cast<const float4*>(gamma + c0);
@@ -222,7 +250,7 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
       const int t = base + r;
       if (t < t_end) {
         const float4 p = *reinterpret_cast<const float4*>(red_sq[r]);
-        const float rstd = 1.0f / sqrtf(((p.x + p.y) + (p.z + p.w)) * (1.0f / C) + eps);
+        const float rstd = dw_rstd<TO>(((p.x + p.y) + (p.z + p.w)) * (1.0f / C) + eps);
         float4 o;
         o.x = (y[r].x - mean[r]) * rstd * gm.x + bt.x;
         o.y = (y[r].y - mean[r]) * rstd * gm.y + bt.y;
@@ -238,10 +266,10 @@ int dwconv7_ln(const float* x, const float* delta, float* x_out, const float* w7
                const float* beta, float eps, void* out, int out_type, int nb, int T, int C, cudaStream_t s) {
   SWC_REQUIRE(C == 512, "dwconv7_ln: only C=512 is built (got %d)", C);
   SWC_REQUIRE(!delta || (x_out && x_out != x), "dwconv7_ln: fused residual needs a distinct output stream buffer");
+  ProfScope ps(KC_DWCONV_LN, s);
   // strips of 64 rows (9 % halo re-reads, served by the L2) when that gives every SM many blocks, else 32
   const int strip = ((long long)nb * ceil_div(T, 64) >= 16 * 148) ? 64 : 32;
   dim3 grid(ceil_div(T, strip), nb);
-  ProfScope ps(KC_DWCONV_LN, s);
   if (out_type == 0) {
     if (delta) dwconv7_ln_kernel<float, true><<<grid, kDwThreads, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (float*)out, T, strip);
     else dwconv7_ln_kernel<float, false><<<grid, kDwThreads, 0, s>>>(x, nullptr, nullptr, w7c, bias, gamma, beta, eps, (float*)out, T, strip);
