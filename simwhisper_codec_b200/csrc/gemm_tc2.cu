@@ -119,6 +119,71 @@ __device__ __forceinline__ void epi4(const uint32_t* acc, const float* sb, const
   }
 }
 
+// One epilogue warp's share of an output tile: its 32 TMEM lanes x kSlice accumulator columns -> bias / activation /
+// gamma -> 128B-swizzled staging boxes -> TMA store (or reduce-add).  `taddr` addresses the warp's first column of the
+// accumulator buffer; the buffer is handed back (arrive on `tempty_addr`) as soon as it is in registers.
+template <int NBUF, int EW, int ACT, bool GAMMA, bool REDUCE, typename TO>
+__device__ __forceinline__ void epilogue_tile(const CUtensorMap* tmO, const Tc2Params& p, uint32_t taddr, uint32_t tempty_addr,
+                                              uint8_t* stage_out, int& obuf, int lane, int lg, int c_base, int b, int m0, int n0) {
+  constexpr int kSlice = BN / (EW / 4);
+  constexpr bool kF32 = sizeof(TO) == 4;
+  constexpr int kOutBytesPerWarp = 32 * 128;
+  const uint32_t sw = (uint32_t)(lane & 7);
+  uint32_t rr[2][32];
+  tmem_ld32(taddr, rr[0]);
+#pragma unroll
+  for (int sub = 0; sub < kSlice / 32; ++sub) {
+    tmem_ld_wait();
+    if (sub + 1 < kSlice / 32) tmem_ld32(taddr + (sub + 1) * 32, rr[(sub + 1) & 1]);
+    if (sub == kSlice / 32 - 1) {                       // accumulator fully in registers: hand the TMEM buffer back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_addr);
+    }
+    const bool new_box = kF32 || (sub & 1) == 0;
+    if (new_box) {                        // the staging box must have been read by its previous TMA store
+      if (lane == 0) tma_store_wait_read<NBUF - 1>();
+      __syncwarp();
+    }
+    const uint32_t box = smem_u32(stage_out + obuf * kOutBytesPerWarp) + (uint32_t)lane * 128u;
+    const int ncol = n0 + c_base + sub * 32;      // first of this sub-chunk's 32 columns
+    const float* sbc = p.bias ? p.bias + ncol : nullptr;
+    const float* sgc = GAMMA ? p.gamma + ncol : nullptr;
+    if constexpr (kF32) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float v[4];
+        epi4<ACT, GAMMA>(&rr[sub & 1][4 * q], sbc ? sbc + 4 * q : nullptr, sgc + 4 * q, ncol + 4 * q + 4 <= p.N, v);
+        st_shared_v4(box + (((uint32_t)q ^ sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                     __float_as_uint(v[3]));
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[8];
+        epi4<ACT, GAMMA>(&rr[sub & 1][8 * q], sbc ? sbc + 8 * q : nullptr, sgc + 8 * q, ncol + 8 * q + 4 <= p.N, v);
+        epi4<ACT, GAMMA>(&rr[sub & 1][8 * q + 4], sbc ? sbc + 8 * q + 4 : nullptr, sgc + 8 * q + 4, ncol + 8 * q + 8 <= p.N, v + 4);
+        const uint32_t chunk = (uint32_t)((sub & 1) * 4 + q);
+        st_shared_v4(box + ((chunk ^ sw) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                     pack_bf16(v[6], v[7]));
+      }
+    }
+    const bool box_done = kF32 || (sub & 1) == 1;
+    if (box_done) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int col = n0 + c_base + (kF32 ? sub * 32 : (sub >> 1) * 64);
+        // REDUCE: the residual add out += tile is done by the L2 (one tile per output element: deterministic)
+        if constexpr (REDUCE) tma_reduce_add_3d(tmO, stage_out + obuf * kOutBytesPerWarp, col, m0 + lg * 32, b);
+        else tma_store_3d(tmO, stage_out + obuf * kOutBytesPerWarp, col, m0 + lg * 32, b);
+        tma_store_commit();
+      }
+      obuf = (obuf + 1 == NBUF) ? 0 : obuf + 1;
+    }
+  }
+}
+
 template <int CG, int STAGES, int NBUF, int EW, int ACT, bool GAMMA, bool REDUCE, typename TO>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -223,11 +288,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int ew = warp - 4;
     const int lg = ew & 3;                    // TMEM lane group of this warp: lanes [32 lg, 32 lg + 32)
     const int c_base = (ew >> 2) * kSlice;    // this warp's accumulator columns
-    constexpr bool kF32 = sizeof(TO) == 4;
     uint8_t* stage_out = smem + L::kOutOff + ew * NBUF * L::kOutBytesPerWarp;
     const uint32_t tempty_leader[2] = {CG == 1 ? smem_u32(&tempty[0]) : mapa(smem_u32(&tempty[0]), 0),
                                        CG == 1 ? smem_u32(&tempty[1]) : mapa(smem_u32(&tempty[1]), 0)};
-    const uint32_t sw = (uint32_t)(lane & 7);
     int acc = 0, obuf = 0;
     uint32_t acc_phase = 0;
     for (int tile = cid; tile < total_tiles; tile += ncl) {
@@ -237,60 +300,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int n0 = (r % p.n_tiles) * BN;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + c_base;
-      uint32_t rr[2][32];
-      tmem_ld32(taddr, rr[0]);
-#pragma unroll
-      for (int sub = 0; sub < kSlice / 32; ++sub) {
-        tmem_ld_wait();
-        if (sub + 1 < kSlice / 32) tmem_ld32(taddr + (sub + 1) * 32, rr[(sub + 1) & 1]);
-        if (sub == kSlice / 32 - 1) {                       // accumulator fully in registers: hand the TMEM buffer back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
-        }
-        const bool new_box = kF32 || (sub & 1) == 0;
-        if (new_box) {                        // the staging box must have been read by its previous TMA store
-          if (lane == 0) tma_store_wait_read<NBUF - 1>();
-          __syncwarp();
-        }
-        const uint32_t box = smem_u32(stage_out + obuf * L::kOutBytesPerWarp) + (uint32_t)lane * 128u;
-        const int ncol = n0 + c_base + sub * 32;      // first of this sub-chunk's 32 columns
-        const float* sbc = p.bias ? p.bias + ncol : nullptr;
-        const float* sgc = GAMMA ? p.gamma + ncol : nullptr;
-        if constexpr (kF32) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float v[4];
-            epi4<ACT, GAMMA>(&rr[sub & 1][4 * q], sbc ? sbc + 4 * q : nullptr, sgc + 4 * q, ncol + 4 * q + 4 <= p.N, v);
-            st_shared_v4(box + (((uint32_t)q ^ sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
-                         __float_as_uint(v[3]));
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float v[8];
-            epi4<ACT, GAMMA>(&rr[sub & 1][8 * q], sbc ? sbc + 8 * q : nullptr, sgc + 8 * q, ncol + 8 * q + 4 <= p.N, v);
-            epi4<ACT, GAMMA>(&rr[sub & 1][8 * q + 4], sbc ? sbc + 8 * q + 4 : nullptr, sgc + 8 * q + 4, ncol + 8 * q + 8 <= p.N, v + 4);
-            const uint32_t chunk = (uint32_t)((sub & 1) * 4 + q);
-            st_shared_v4(box + ((chunk ^ sw) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                         pack_bf16(v[6], v[7]));
-          }
-        }
-        const bool box_done = kF32 || (sub & 1) == 1;
-        if (box_done) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            const int col = n0 + c_base + (kF32 ? sub * 32 : (sub >> 1) * 64);
-            // REDUCE: the residual add out += tile is done by the L2 (one tile per output element: deterministic)
-            if constexpr (REDUCE) tma_reduce_add_3d(&tmO, stage_out + obuf * L::kOutBytesPerWarp, col, m0 + lg * 32, b);
-            else tma_store_3d(&tmO, stage_out + obuf * L::kOutBytesPerWarp, col, m0 + lg * 32, b);
-            tma_store_commit();
-          }
-          obuf = (obuf + 1 == NBUF) ? 0 : obuf + 1;
-        }
-      }
+      epilogue_tile<NBUF, EW, ACT, GAMMA, REDUCE, TO>(&tmO, p, tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + c_base,
+                                                      tempty_leader[acc], stage_out, obuf, lane, lg, c_base, b, m0, n0);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -398,7 +409,7 @@ bool gemm_tc2_eligible(const GemmDesc& d) {
          d.tap_k % BK == 0 && ((uintptr_t)e.out & 15) == 0;
 }
 
-// variant: 1 = single-CTA tiles + TMA store, 2 = CTA pairs
+// variant: 1 = single-CTA tiles + TMA store, 2 = CTA pairs, 3 = CTA pairs with 16 epilogue warps
 int gemm_tc2(const GemmDesc& d, int out_type, int num_sms, int variant, cudaStream_t s) {
   SWC_REQUIRE(gemm_tc2_eligible(d), "gemm_tc2: problem not eligible (residual/out2/act/N)");
   SWC_REQUIRE(d.m_rows > 0 && d.nb > 0, "gemm_tc2: empty problem");
