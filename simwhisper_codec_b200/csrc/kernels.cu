@@ -138,6 +138,36 @@ __device__ __forceinline__ float warp_sum8(const float (&v)[8], int lane) {
   c += __shfl_xor_sync(0xffffffffu, c, 1);
   return c;
 }
+// four channels as two packed fp32 pairs: fma / mul / add / sub .f32x2 (sm_100) handle two lanes per issued instruction
+struct F4P { unsigned long long lo, hi; };
+__device__ __forceinline__ unsigned long long pk2f(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2f(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ F4P f4p(float4 v) { return F4P{pk2f(v.x, v.y), pk2f(v.z, v.w)}; }
+__device__ __forceinline__ F4P f4p(float v) { const unsigned long long p = pk2f(v, v); return F4P{p, p}; }
+__device__ __forceinline__ float4 f4(F4P v) { float4 r; upk2f(v.lo, r.x, r.y); upk2f(v.hi, r.z, r.w); return r; }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ F4P fma(F4P a, F4P b, F4P c) { return F4P{fma2(a.lo, b.lo, c.lo), fma2(a.hi, b.hi, c.hi)}; }
+__device__ __forceinline__ F4P mul(F4P a, F4P b) { return F4P{mul2(a.lo, b.lo), mul2(a.hi, b.hi)}; }
+__device__ __forceinline__ F4P sub(F4P a, F4P b) { return F4P{sub2(a.lo, b.lo), sub2(a.hi, b.hi)}; }
+
 template <typename TO>
 __device__ __forceinline__ float dw_rstd(float var_eps) {
   if constexpr (sizeof(TO) == 2) return rsqrtf(var_eps);      // bf16 output: MUFU.RSQ (1 ulp) instead of sqrt + divide
@@ -172,7 +202,7 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
   // (each thread reads back only the taps it wrote: no barrier needed)
 
   // window[j] holds s(row base - 3 + j); rows outside [0, T) are the convolution's zero padding
-  float4 win[R + 6];
+  F4P win[R + 6];
   auto load_row = [&](int t, bool own) -> float4 {
     if (t < 0 || t >= T) return zero4;
     float4 v = *reinterpret_cast<const float4*>(xb + (long long)t * C);
@@ -183,7 +213,7 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
     return v;
   };
 #pragma unroll
-  for (int j = 0; j < 6; ++j) win[j] = load_row(t0 - 3 + j, j >= 3);
+  for (int j = 0; j < 6; ++j) win[j] = f4p(load_row(t0 - 3 + j, j >= 3));
 
   // rows base+3 .. base+10 of the coming step (the last three of the strip's final step belong to the next strip);
   // the loads of step n+1 are issued before the LayerNorm phase of step n so that their latency hides behind it
@@ -198,6 +228,9 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
     }
   };
   fetch(t0);
+  const F4P bsp = f4p(bs);
+  const F4P gmp = f4p(*reinterpret_cast<const float4*>(gamma + c0));
+  const F4P btp = f4p(*reinterpret_cast<const float4*>(beta + c0));
   for (int base = t0; base < t_end; base += R) {
 #pragma unroll
     for (int j = 0; j < R; ++j) {
@@ -207,24 +240,27 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
         v = f4_add(v, dv[j]);
         if (t < t_end) *reinterpret_cast<float4*>(xo + (long long)t * C) = v;
       }
-      win[6 + j] = v;
+      win[6 + j] = f4p(v);
     }
-    // conv + bias for rows base .. base+7
-    float4 y[R];
+    // conv + bias for rows base .. base+7 (same fused multiply-adds in the same order as the scalar form, two per instruction)
+    F4P y[R];
     float psum[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) y[r] = bs;
+    for (int r = 0; r < R; ++r) y[r] = bsp;
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
-      const float4 wk = *reinterpret_cast<const float4*>(sw + k * C + c0);
+      const F4P wk = f4p(*reinterpret_cast<const float4*>(sw + k * C + c0));
 #pragma unroll
-      for (int r = 0; r < R; ++r) y[r] = f4_fma(win[r + k], wk, y[r]);
+      for (int r = 0; r < R; ++r) y[r] = fma(win[r + k], wk, y[r]);
     }
 #pragma unroll
     for (int j = 0; j < 6; ++j) win[j] = win[j + R];
     if (base + R < t_end) fetch(base + R);
 #pragma unroll
-    for (int r = 0; r < R; ++r) psum[r] = (y[r].x + y[r].y) + (y[r].z + y[r].w);
+    for (int r = 0; r < R; ++r) {
+      const float4 v = f4(y[r]);
+      psum[r] = (v.x + v.y) + (v.z + v.w);
+    }
     {
       const float tot = warp_sum8(psum, lane);          // lane l: row l >> 2
       if ((lane & 3) == 0) red_sum[lane >> 2][warp] = tot;
@@ -235,28 +271,23 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
     for (int r = 0; r < R; ++r) {
       const float4 p = *reinterpret_cast<const float4*>(red_sum[r]);
       mean[r] = ((p.x + p.y) + (p.z + p.w)) * (1.0f / C);
-      const float dx = y[r].x - mean[r], dy = y[r].y - mean[r], dz = y[r].z - mean[r], dw = y[r].w - mean[r];
-      psum[r] = fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw);
+      y[r] = sub(y[r], f4p(mean[r]));                   // centred from here on
+      float a, b2;
+      upk2f(fma2(y[r].lo, y[r].lo, mul2(y[r].hi, y[r].hi)), a, b2);   // (dx^2 + dz^2, dy^2 + dw^2)
+      psum[r] = a + b2;
     }
     {
       const float tot = warp_sum8(psum, lane);
       if ((lane & 3) == 0) red_sq[lane >> 2][warp] = tot;
     }
     __syncthreads();
-    const float4 gm = *reinterpret_cast<const float4*>(gamma + c0);
-    const float4 bt = *reinterpret_cast<const float4*>(beta + c0);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int t = base + r;
       if (t < t_end) {
         const float4 p = *reinterpret_cast<const float4*>(red_sq[r]);
         const float rstd = dw_rstd<TO>(((p.x + p.y) + (p.z + p.w)) * (1.0f / C) + eps);
-        float4 o;
-        o.x = (y[r].x - mean[r]) * rstd * gm.x + bt.x;
-        o.y = (y[r].y - mean[r]) * rstd * gm.y + bt.y;
-        o.z = (y[r].z - mean[r]) * rstd * gm.z + bt.z;
-        o.w = (y[r].w - mean[r]) * rstd * gm.w + bt.w;
-        store4(ob + (long long)t * C, o);
+        store4(ob + (long long)t * C, f4(fma(mul(y[r], f4p(rstd)), gmp, btp)));
       }
     }
   }
