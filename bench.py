@@ -261,9 +261,12 @@ def main():
     clocks = sampler.stop()
     value = world * B * 30.0 / (ms * 1e-3)
 
-    # per-kernel-class device time over the same step with CUDA events around every launch
-    lib.swc_profile(1)
+    # per-kernel-class device time over the same step with CUDA events around every launch.  An un-profiled step runs
+    # directly in front of it (no synchronisation in between), so the profiled step sees the steady-state clocks of the
+    # power-capped timed region rather than the boost of a GPU that has just been idle.
     barrier()
+    step_resident()
+    lib.swc_profile(1)
     step_resident()
     torch.cuda.synchronize()
     lib.swc_profile_read(ms_cls, n_cls, 8)

@@ -20,14 +20,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (long long)nb * t_out) return;
-  const int b = (int)(row / t_out), t = (int)(row % t_out);
+  const int b = (int)((unsigned)row / (unsigned)t_out), t = (int)row - b * t_out;     // nb * t_out < 2^31 (checked by the launcher)
   TO* o = out + row * C;
   const bool in_range = t < t_in;
-  bool live = in_range;
-  if (live && lens) live = (long long)t < lens[b];
+  // the length is fetched together with the row, not before it: a row load that waits for lens[b] pays the L2 latency
+  // twice (rows beyond the length are then read for nothing; variable-length batches run the packed path instead)
+  const long long len_b = (in_range && lens) ? lens[b] : (long long)t_in;
   const long long irow = ((long long)b * t_in + t) * C;
   float v[NCH][8];
-  if (in_range && (live || delta)) {
+  if (in_range) {
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int c0 = (c * 32 + lane) * 8;
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       }
     }
   }
+  const bool live = in_range && (long long)t < len_b;
   if (!live) {
     float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -75,6 +77,7 @@ template <typename TO>
 static int layernorm_t(const float* in, const float* delta, float* h_out, void* out, const float* g, const float* b, float eps,
                        int nb, int t_in, int t_out, int C, const long long* lens, cudaStream_t s) {
   const long long rows = (long long)nb * t_out;
+  SWC_REQUIRE(rows < (1ll << 31), "layernorm: too many rows (%lld)", rows);
   const int warps = 8;
   dim3 grid((unsigned)ceil_div_ll(rows, warps));
   ProfScope ps(KC_LAYERNORM, s);
