@@ -18,6 +18,7 @@
 // time share A rows in L2.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
@@ -98,24 +99,58 @@ __device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
   return r;
 }
 // 4 accumulator columns -> (act(acc + bias)) * gamma.  bias / gamma are read straight from global memory: the
-// address is uniform across the warp (one L1 transaction per load) and the vectors stay L1-resident.
-template <int ACT, bool GAMMA>
+// address is uniform across the warp (one L1 transaction per load) and the vectors stay L1-resident.  FAST: the whole
+// 32-column chunk lies inside N and a bias exists, so no per-chunk predicates (the common case; the general form costs
+// a compare, a select and a register clear per four columns).
+template <int ACT, bool GAMMA, bool FAST>
 __device__ __forceinline__ void epi4(const uint32_t* acc, const float* sb, const float* sg, bool in_range, float* v) {
-  const float4 b4 = (sb && in_range) ? __ldg(reinterpret_cast<const float4*>(sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 b4;
+  if constexpr (FAST) b4 = __ldg(reinterpret_cast<const float4*>(sb));
+  else b4 = (sb && in_range) ? __ldg(reinterpret_cast<const float4*>(sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
   unsigned long long lo, hi;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(lo) : "l"(pack_f32x2(__uint_as_float(acc[0]), __uint_as_float(acc[1]))), "l"(pack_f32x2(b4.x, b4.y)));
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(hi) : "l"(pack_f32x2(__uint_as_float(acc[2]), __uint_as_float(acc[3]))), "l"(pack_f32x2(b4.z, b4.w)));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(v[0]), "=f"(v[1]) : "l"(lo));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(v[2]), "=f"(v[3]) : "l"(hi));
   if constexpr (ACT == 2) {
-    gelu_fast2(v[0], v[1]);
-    gelu_fast2(v[2], v[3]);
-  } else if constexpr (ACT == 1) {
-    v[0] = gelu_erf(v[0]); v[1] = gelu_erf(v[1]); v[2] = gelu_erf(v[2]); v[3] = gelu_erf(v[3]);
+    lo = gelu_fast2(lo);
+    hi = gelu_fast2(hi);
   }
   if constexpr (GAMMA) {
-    const float4 g4 = in_range ? __ldg(reinterpret_cast<const float4*>(sg)) : make_float4(1.f, 1.f, 1.f, 1.f);
-    v[0] *= g4.x; v[1] *= g4.y; v[2] *= g4.z; v[3] *= g4.w;
+    float4 g4;
+    if constexpr (FAST) g4 = __ldg(reinterpret_cast<const float4*>(sg));
+    else g4 = in_range ? __ldg(reinterpret_cast<const float4*>(sg)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(lo) : "l"(lo), "l"(pack_f32x2(g4.x, g4.y)));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(hi) : "l"(hi), "l"(pack_f32x2(g4.z, g4.w)));
+  }
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v[0]), "=f"(v[1]) : "l"(lo));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v[2]), "=f"(v[3]) : "l"(hi));
+  if constexpr (ACT == 1) {
+    v[0] = gelu_erf(v[0]); v[1] = gelu_erf(v[1]); v[2] = gelu_erf(v[2]); v[3] = gelu_erf(v[3]);
+  }
+}
+
+// 32 accumulator columns of one row -> epilogue math -> the row's 128-byte line of the staging box (16-byte chunks
+// XOR-swizzled by the row).  bf16 results fill half a line per call (`half` selects which).
+template <int ACT, bool GAMMA, bool FAST, bool kF32>
+__device__ __forceinline__ void convert_sub(const uint32_t (&acc)[32], const float* sbc, const float* sgc, int ncol, int N,
+                                            uint32_t box, uint32_t sw, int half) {
+  if constexpr (kF32) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float v[4];
+      epi4<ACT, GAMMA, FAST>(&acc[4 * q], sbc ? sbc + 4 * q : nullptr, sgc + 4 * q, ncol + 4 * q + 4 <= N, v);
+      st_shared_v4(box + (((uint32_t)q ^ sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                   __float_as_uint(v[3]));
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[8];
+      epi4<ACT, GAMMA, FAST>(&acc[8 * q], sbc ? sbc + 8 * q : nullptr, sgc + 8 * q, ncol + 8 * q + 4 <= N, v);
+      epi4<ACT, GAMMA, FAST>(&acc[8 * q + 4], sbc ? sbc + 8 * q + 4 : nullptr, sgc + 8 * q + 4, ncol + 8 * q + 8 <= N, v + 4);
+      const uint32_t chunk = (uint32_t)(half * 4 + q);
+      st_shared_v4(box + ((chunk ^ sw) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                   pack_bf16(v[6], v[7]));
+    }
   }
 }
 
@@ -149,25 +184,8 @@ __device__ __forceinline__ void epilogue_tile(const CUtensorMap* tmO, const Tc2P
     const int ncol = n0 + c_base + sub * 32;      // first of this sub-chunk's 32 columns
     const float* sbc = p.bias ? p.bias + ncol : nullptr;
     const float* sgc = GAMMA ? p.gamma + ncol : nullptr;
-    if constexpr (kF32) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float v[4];
-        epi4<ACT, GAMMA>(&rr[sub & 1][4 * q], sbc ? sbc + 4 * q : nullptr, sgc + 4 * q, ncol + 4 * q + 4 <= p.N, v);
-        st_shared_v4(box + (((uint32_t)q ^ sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
-                     __float_as_uint(v[3]));
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v[8];
-        epi4<ACT, GAMMA>(&rr[sub & 1][8 * q], sbc ? sbc + 8 * q : nullptr, sgc + 8 * q, ncol + 8 * q + 4 <= p.N, v);
-        epi4<ACT, GAMMA>(&rr[sub & 1][8 * q + 4], sbc ? sbc + 8 * q + 4 : nullptr, sgc + 8 * q + 4, ncol + 8 * q + 8 <= p.N, v + 4);
-        const uint32_t chunk = (uint32_t)((sub & 1) * 4 + q);
-        st_shared_v4(box + ((chunk ^ sw) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                     pack_bf16(v[6], v[7]));
-      }
-    }
+    if (sbc != nullptr && ncol + 32 <= p.N) convert_sub<ACT, GAMMA, true, kF32>(rr[sub & 1], sbc, sgc, ncol, p.N, box, sw, sub & 1);
+    else convert_sub<ACT, GAMMA, false, kF32>(rr[sub & 1], sbc, sgc, ncol, p.N, box, sw, sub & 1);
     const bool box_done = kF32 || (sub & 1) == 1;
     if (box_done) {
       fence_proxy_async_smem();
@@ -416,6 +434,10 @@ int gemm_tc2(const GemmDesc& d, int out_type, int num_sms, int variant, cudaStre
   SWC_REQUIRE(((uintptr_t)d.A & 15) == 0 && ((uintptr_t)d.W & 15) == 0, "gemm_tc2: operands must be 16-byte aligned");
   if (variant == 1) return dispatch2<1, 4, 1, 8>(d, out_type, num_sms, s);
   if (variant == 3) return dispatch2<2, 5, 1, 16>(d, out_type, num_sms, s);  // 16 epilogue warps (64 columns each), 5-stage ring
+  // Short K with a bf16 result (pwconv1, to_stacked: 8 K slabs per tile, two staging boxes per warp and tile): the tile
+  // is epilogue-paced, so a second staging box per warp (no wait for the previous TMA store in mid-tile) is worth more
+  // than the sixth operand stage (+2.7 % on pwconv1; the long-K fp32 shapes lose 5 % with it and keep six stages).
+  if (out_type == 1 && d.n_taps * d.tap_k <= 8 * BK) return dispatch2<2, 5, 2, 8>(d, out_type, num_sms, s);
   return dispatch2<2, 6, 1, 8>(d, out_type, num_sms, s);                     // deepest operand ring that fits 227 KB
 }
 
