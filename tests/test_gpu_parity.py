@@ -157,6 +157,29 @@ def test_full_window_vs_oracle_fp32(model32, sd_ex):
     assert snr_db(ref_wav["y"], out["y"].cpu()) >= 40.0
 
 
+def test_config1_batch64_fp32_indices(model32, sd_ex):
+    """BASELINE configs[1]: encoder + quantizer only, batch 64 x 30 s, fp32 mode.  Two of the 64 windows are checked
+    against the CPU oracle (bit-exact indices up to near-tie flips < 0.1 %), the rest through batch independence (a
+    window's codes do not depend on its neighbours) and the code alphabet (8 groups x 2016 levels)."""
+    B = 64
+    x = torch.stack([synthetic_wave(7000 + i, 480000) for i in range(B)])[:, None, :]
+    lens = torch.full((B,), 480000)
+    r = model32.inference_tokenize(x.cuda(), lens.cuda())
+    codes = r["codes"].cpu()
+    assert codes.shape == (8, B, 375) and codes.dtype == torch.int32
+    assert r["codes_lengths"].tolist() == [375] * B
+    assert int(codes.min()) >= 0 and int(codes.max()) < 2016
+    with torch.inference_mode():
+        ref = port.tokenize(sd_ex, x[[0, 63]], lens[[0, 63]])
+    flips = (codes[:, [0, 63]] != ref["codes"]).float().mean().item()
+    assert flips < 1e-3, flips
+    for i in (17, 40):
+        solo = model32.inference_tokenize(x[i:i + 1].cuda(), lens[i:i + 1].cuda())
+        assert torch.equal(solo["codes"][:, 0].cpu(), codes[:, i])
+    # distinct inputs give distinct code streams (no aliasing of batch slots)
+    assert len({codes[:, i].numpy().tobytes() for i in range(B)}) == B
+
+
 def test_bf16_full_window_properties(model16, model32, gen_params, sd_ex):
     """bf16 (tcgen05) mode at full window size: batch independence, sub-batch independence, and its distance from the
     fp32 path on the same device (reported; loose bounds)."""
