@@ -428,12 +428,23 @@ class AudioCodec(nn.Module):
     def decode_jobs(self, codes_list, jobs, device) -> torch.Tensor:
         """Detokenize decode windows that share one pad length T' -> wav (len(jobs), 1280 T')."""
         Tp = jobs[0].pad_len
+        # longest window first: with the lengths in descending order the library runs Vocos (46 % of the FLOPs, no
+        # length masking in the reference) only over each run's valid frames plus its receptive-field halo instead of
+        # over all T' frames of every window; samples beyond a window's halo are left unwritten (callers keep valid ones)
+        order = sorted(range(len(jobs)), key=lambda k: -jobs[k].n_valid)
         ct = torch.zeros((self.num_groups, len(jobs), Tp), dtype=torch.int64, device=device)
-        for k, j in enumerate(jobs):
-            ct[:, k, : j.n_valid] = torch.as_tensor(codes_list[j.item])[:, j.start:j.start + j.n_valid].to(
+        for r, k in enumerate(order):
+            j = jobs[k]
+            ct[:, r, : j.n_valid] = torch.as_tensor(codes_list[j.item])[:, j.start:j.start + j.n_valid].to(
                 device=device, dtype=torch.int64, non_blocking=True)
-        cl = torch.tensor([j.n_valid for j in jobs], dtype=torch.int64).to(device, non_blocking=True)
-        return self._detokenize(ct, cl, host_lens=[j.n_valid for j in jobs])[0]
+        hl = [jobs[k].n_valid for k in order]
+        cl = torch.tensor(hl, dtype=torch.int64).to(device, non_blocking=True)
+        wav = self._detokenize(ct, cl, host_lens=hl)[0]
+        if order == list(range(len(jobs))):
+            return wav
+        inv = torch.empty(len(jobs), dtype=torch.int64)
+        inv[torch.tensor(order)] = torch.arange(len(jobs))
+        return wav.index_select(0, inv.to(device, non_blocking=True))
 
     @torch.inference_mode()
     def encode(self, wav_list, overlap_seconds=10, device=torch.device("cuda")):

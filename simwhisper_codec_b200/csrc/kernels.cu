@@ -641,7 +641,7 @@ int mel_finalize(const float* logmel, const float* item_max, int nb, float* mel_
 // out[s] = sum_t frames[t][p-160t] / sum_t w^2[p-160t],  p = s + 240, t in the <=4 overlapping frames.
 // ================================================================================================
 __global__ void istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ win_sq, int T,
-                                 float* __restrict__ wav) {
+                                 float* __restrict__ wav, long long wav_stride) {
   __shared__ float w2[640];
   for (int i = threadIdx.x; i < 640; i += blockDim.x) w2[i] = win_sq[i];
   __syncthreads();
@@ -658,13 +658,13 @@ __global__ void istft_ola_kernel(const float* __restrict__ frames, const float* 
     acc += frames[((long long)b * T + t) * 640 + n];
     env += w2[n];
   }
-  wav[(long long)b * L + sidx] = acc / env;
+  wav[(long long)b * wav_stride + sidx] = acc / env;
 }
 
-int istft_ola(const float* frames, const float* win_sq, int nb, int T, float* wav, cudaStream_t s) {
+int istft_ola(const float* frames, const float* win_sq, int nb, int T, float* wav, long long wav_stride, cudaStream_t s) {
   dim3 grid(ceil_div(160 * T, 256), nb);
   ProfScope ps(KC_MISC, s);
-  istft_ola_kernel<<<grid, 256, 0, s>>>(frames, win_sq, T, wav);
+  istft_ola_kernel<<<grid, 256, 0, s>>>(frames, win_sq, T, wav, wav_stride);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -42,7 +42,8 @@ int mel_finalize(const float* logmel /*(nb,3000,80)*/, const float* item_max, in
                  void* mel_cl, int cl_type, int cl_pitch, cudaStream_t s);
 
 // iSTFT overlap-add ("same" padding): frames (nb,T,640) fp32 -> wav (nb,160T) fp32
-int istft_ola(const float* frames, const float* win_sq /*[640]*/, int nb, int T, float* wav, cudaStream_t s);
+// wav rows are wav_stride floats apart (>= 160 T)
+int istft_ola(const float* frames, const float* win_sq /*[640]*/, int nb, int T, float* wav, long long wav_stride, cudaStream_t s);
 
 // ---- ragged (packed valid tokens) transformer path: per-item token counts known on the host --------------------
 constexpr int kMaxRagged = 128;

@@ -321,9 +321,13 @@ int decoder_cl(Ctx& c, float* h, const long long* lens, int nb, int T, void* mel
 // ------------------------------------------------------------------------------------------------
 // Vocos backbone + ISTFT head (reference modules.py:1492-1504, 1229-1248, 1064-1082, 831-886)
 // mel_cl (nb,Tv,128) act type -> wav fp32 (nb,160 Tv).  No length masking anywhere.
+// Tv_in / wav_stride (0 = dense): the caller may run only the first Tv frames of items that are Tv_in frames long; the
+// convolutions then see zeros beyond frame Tv - 1 exactly as at the end of a sequence (TMA zero fill / dwconv padding).
 // ------------------------------------------------------------------------------------------------
-int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav) {
+int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav, int Tv_in, long long wav_stride) {
   const Model& m = *c.m;
+  if (Tv_in <= 0) Tv_in = Tv;
+  if (wav_stride <= 0) wav_stride = 160ll * Tv;
   const int V = m.voc_dim, I = m.voc_inter, MP = m.mel_pitch, at = m.act_type();
   const long long rows = (long long)nb * Tv;
   const int NP = m.voc_head.N;
@@ -338,7 +342,7 @@ int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav) {
     void* g = region;
     float* e = (float*)region;     // embed output (fp32) lives in the region until the first LayerNorm
     {
-      GemmDesc d = base_desc(mel_cl, MP, (long long)Tv * MP, Tv, MP, Tv, nb, m.voc_embed);
+      GemmDesc d = base_desc(mel_cl, MP, (long long)Tv_in * MP, Tv, MP, Tv, nb, m.voc_embed);
       d.n_taps = 7; d.tap_k = MP;
       for (int k = 0; k < 7; ++k) { d.tap_row[k] = k - 3; d.tap_col[k] = 0; }
       set_out(d, e, V, (long long)Tv * V);
@@ -387,7 +391,7 @@ int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav) {
       set_out(d, frames, m.n_fft, 0);
       SWC_TRY(gemm_simt(d, EPI_STORE, 0, 0, c.s));
     }
-    SWC_TRY(istft_ola(frames, m.win_sq, nb, Tv, wav, c.s));
+    SWC_TRY(istft_ola(frames, m.win_sq, nb, Tv, wav, wav_stride, c.s));
   }
   c.ws.release(mark);
   return 0;
@@ -477,7 +481,34 @@ int detokenize_chain(Ctx& c, const float* zq_cl, const long long* code_lens, int
   SWC_TRY(lens_affine(c, code_lens, out_lens, nb, 1280, 0, 1));
   SWC_TRY(upsample_cl(c, zq_cl, nb, Tc, h));
   SWC_TRY(decoder_cl(c, h, tok_lens, nb, T, mel_cl));
-  SWC_TRY(vocos_cl(c, mel_cl, nb, Tv, wav));
+  // Vocos has no length masking (reference modules.py:1492-1504) but its receptive field is finite: an output sample
+  // of frame t reads frames <= t + 1 of the last block, each of the 24 depthwise convolutions and the embedding add 3:
+  // everything a valid sample depends on lies below frame 8 len + 77.  When the caller passed host lengths in
+  // descending order (decode_jobs does), items are grouped into runs of similar length and each run computes only
+  // min(Tv, 8 len_max + 80) frames; the frames beyond see the cut as a sequence end, which can reach valid samples
+  // only from frame 8 len + 5 on.  Valid samples are bit-identical to the full-length computation.
+  bool bucketed = false;
+  if (c.rag != nullptr && c.rag->nb == nb && !c.dry && at == 1) {
+    bucketed = true;
+    for (int b = 1; b < nb; ++b) bucketed = bucketed && c.rag->len[b] <= c.rag->len[b - 1];
+  }
+  if (bucketed) {
+    constexpr int kHalo = 80;
+    constexpr long long kMinRows = 40000;            // >= two waves of 256-row tile pairs per GEMM launch
+    auto need = [&](int b) { return std::min(Tv, 2 * c.rag->len[b] + kHalo); };      // len = tokens = 4 x code frames
+    const size_t mel_row = (size_t)m.mel_pitch * esz(at);
+    for (int b0 = 0; b0 < nb;) {
+      const int tv = (need(b0) + 7) / 8 * 8 > Tv ? Tv : (need(b0) + 7) / 8 * 8;
+      int b1 = b0 + 1;
+      while (b1 < nb && ((long long)(b1 - b0) * tv < kMinRows || need(b1) * 10 >= tv * 8)) ++b1;
+      if ((long long)(nb - b1) * tv < kMinRows / 2) b1 = nb;                            // no tiny last run
+      SWC_TRY(vocos_cl(c, (const char*)mel_cl + (size_t)b0 * Tv * mel_row, b1 - b0, tv, wav + (long long)b0 * 160 * Tv, Tv,
+                       160ll * Tv));
+      b0 = b1;
+    }
+  } else {
+    SWC_TRY(vocos_cl(c, mel_cl, nb, Tv, wav));
+  }
   c.ws.release(mark);
   return 0;
 }
