@@ -576,21 +576,34 @@ int mel_pad(const float* wav, long long wav_stride, int wav_cols, const long lon
   return 0;
 }
 
-__global__ void mel_frames_split_kernel(const float* __restrict__ padded, bf16* __restrict__ frames) {
-  // one block = one frame; thread n < 448 handles sample n of the frame
-  const int t = blockIdx.x, b = blockIdx.y, n = threadIdx.x;
-  float x = 0.f;
-  if (n < 400) x = padded[(long long)b * (kMelSamples + 2 * kMelPad) + (long long)t * 160 + n];
-  const bf16 a1 = __float2bfloat16_rn(x);
-  const float r1 = x - __bfloat162float(a1);
-  const bf16 a2 = __float2bfloat16_rn(r1);
-  const bf16 a3 = __float2bfloat16_rn(r1 - __bfloat162float(a2));
-  bf16* o = frames + ((long long)b * kMelFrames + t) * (3 * 448) + n;
-  o[0] = a1; o[448] = a2; o[896] = a3;
+__global__ void __launch_bounds__(448) mel_frames_split_kernel(const float* __restrict__ padded, bf16* __restrict__ frames) {
+  // one block = 8 frames; a thread splits 8 consecutive samples of one frame into the three bf16 terms and writes each
+  // plane with one 16-byte store (frame starts are 640 bytes apart, so the two float4 loads are aligned)
+  const int f = threadIdx.x / 56, g = threadIdx.x - f * 56;
+  const int t = blockIdx.x * 8 + f, b = blockIdx.y;
+  if (t >= kMelFrames) return;
+  float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (g < 50) {
+    const float* src = padded + (long long)b * (kMelSamples + 2 * kMelPad) + (long long)t * 160 + g * 8;
+    const float4 u = *reinterpret_cast<const float4*>(src), v = *reinterpret_cast<const float4*>(src + 4);
+    x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
+  }
+  __align__(16) bf16 a1[8], a2[8], a3[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a1[i] = __float2bfloat16_rn(x[i]);
+    const float r1 = x[i] - __bfloat162float(a1[i]);
+    a2[i] = __float2bfloat16_rn(r1);
+    a3[i] = __float2bfloat16_rn(r1 - __bfloat162float(a2[i]));
+  }
+  bf16* o = frames + ((long long)b * kMelFrames + t) * (3 * 448) + g * 8;
+  *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(a1);
+  *reinterpret_cast<uint4*>(o + 448) = *reinterpret_cast<const uint4*>(a2);
+  *reinterpret_cast<uint4*>(o + 896) = *reinterpret_cast<const uint4*>(a3);
 }
-
 int mel_frames_split(const float* padded, int nb, bf16* frames, cudaStream_t s) {
-  dim3 grid(kMelFrames, nb);
+  SWC_REQUIRE(((uintptr_t)padded & 15) == 0 && ((uintptr_t)frames & 15) == 0, "mel_frames_split: buffers must be 16-byte aligned");
+  dim3 grid(ceil_div(kMelFrames, 8), nb);
   ProfScope ps(KC_MISC, s);
   mel_frames_split_kernel<<<grid, 448, 0, s>>>(padded, frames);
   SWC_CHECK_CUDA(cudaGetLastError());
@@ -640,29 +653,33 @@ int mel_finalize(const float* logmel, const float* item_max, int nb, float* mel_
 // iSTFT overlap-add with "same" padding (reference modules.py:861-884): n_fft 640, hop 160.
 // out[s] = sum_t frames[t][p-160t] / sum_t w^2[p-160t],  p = s + 240, t in the <=4 overlapping frames.
 // ================================================================================================
-__global__ void istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ win_sq, int T,
-                                 float* __restrict__ wav, long long wav_stride) {
-  __shared__ float w2[640];
+__global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ win_sq, int T,
+                                                        float* __restrict__ wav, long long wav_stride) {
+  // one thread = 4 consecutive output samples: hop, trim and frame length are multiples of 4, so the four samples sit in
+  // the same (<= 4) frames and every access is a float4
+  __shared__ __align__(16) float w2[640];
   for (int i = threadIdx.x; i < 640; i += blockDim.x) w2[i] = win_sq[i];
   __syncthreads();
   const int b = blockIdx.y;
-  const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int L = 160 * T;
   if (sidx >= L) return;
   const int p = sidx + 240;
   const int t_hi = min(T - 1, p / 160);
   const int t_lo = max(0, (p - 639 + 159) / 160);
-  float acc = 0.f, env = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), env = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int t = t_lo; t <= t_hi; ++t) {
     const int n = p - 160 * t;
-    acc += frames[((long long)b * T + t) * 640 + n];
-    env += w2[n];
+    const float4 f = *reinterpret_cast<const float4*>(frames + ((long long)b * T + t) * 640 + n);
+    const float4 w = *reinterpret_cast<const float4*>(w2 + n);
+    acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+    env.x += w.x; env.y += w.y; env.z += w.z; env.w += w.w;
   }
-  wav[(long long)b * wav_stride + sidx] = acc / env;
+  *reinterpret_cast<float4*>(wav + (long long)b * wav_stride + sidx) = make_float4(acc.x / env.x, acc.y / env.y, acc.z / env.z, acc.w / env.w);
 }
-
 int istft_ola(const float* frames, const float* win_sq, int nb, int T, float* wav, long long wav_stride, cudaStream_t s) {
-  dim3 grid(ceil_div(160 * T, 256), nb);
+  SWC_REQUIRE(((uintptr_t)frames & 15) == 0 && ((uintptr_t)wav & 15) == 0 && wav_stride % 4 == 0, "istft_ola: buffers must be 16-byte aligned");
+  dim3 grid(ceil_div(40 * T, 256), nb);
   ProfScope ps(KC_MISC, s);
   istft_ola_kernel<<<grid, 256, 0, s>>>(frames, win_sq, T, wav, wav_stride);
   SWC_CHECK_CUDA(cudaGetLastError());
