@@ -145,6 +145,9 @@ int swc_test_gemm(int backend /*0 simt fp32, 1 simt bf16, 2 tcgen05 bf16 (gen 1)
 void swc_set_gemm_variant(int variant);
 int swc_test_attention(int backend /*0 simt fp32, 1 simt bf16, 2 mma.sync bf16, 3 tcgen05 bf16*/, const void* qkv, void* out,
                        const int64_t* lens, int batch, int T, int heads, void* stream);
+/* profiling hook (tools/attn_trace.py): enable != 0 arms per-phase clock64 stamps of CTA 0 for the next tcgen05 attention
+   launch; enable == 0 synchronises, copies up to n stamps (3 x 4096 slots) to host_out and disarms.  0 on success. */
+int swc_debug_attn_trace(int enable, long long* host_out, int n);
 
 #ifdef __cplusplus
 }

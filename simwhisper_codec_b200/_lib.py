@@ -48,6 +48,7 @@ SIGNATURES = {
     "swc_test_gemm": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "swc_set_gemm_variant": (None, [_i]),
     "swc_test_attention": (_i, [_i, _p, _p, _p, _i, _i, _i, _p]),
+    "swc_debug_attn_trace": (_i, [_i, _p, _i]),
 }
 
 _lib = None
