@@ -74,20 +74,23 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
-        sm, mx, reasons = [], 0, set()
+        sm, pw, mx, reasons = [], [], 0, set()
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
+                pw.append(float(r[3]))
                 mx = max(mx, float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 continue
-        sm.sort()
-        busy = sm[len(sm) // 2:] if sm else []          # upper half = samples under load
+        # samples under load = those drawing at least 70 % of the highest power seen (idle samples read the boost clock)
+        top = max(pw) if pw else 0.0
+        busy = sorted(c for c, w in zip(sm, pw) if w >= 0.7 * top)
         return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(busy),
+                "power_w_max": top or None}
 
 
 def cpu_reference_run(steps, warmup, windows_per_step=1):
