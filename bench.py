@@ -123,7 +123,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="30 s windows per GPU per step")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3"])
     ap.add_argument("--max-batch", type=int, default=int(os.environ.get("SWC_MAX_BATCH", 256)),
                     help="windows per kernel launch (the 256-window step runs as 256/max_batch sub-batches)")
     ap.add_argument("--e2e-chunk", type=int, default=256,

@@ -29,7 +29,9 @@ extern "C" {
 
 typedef struct swc_model swc_model;
 
-enum { SWC_PRECISION_FP32 = 0, SWC_PRECISION_BF16 = 1 };
+/* BF16X3: fp32 activations and epilogues as in FP32, dense contractions on the tensor cores as three bf16 products
+   (a_hi w_hi + a_hi w_lo + a_lo w_hi, fp32 accumulation: relative error ~2^-17); attention, mel and iSTFT stay fp32 */
+enum { SWC_PRECISION_FP32 = 0, SWC_PRECISION_BF16 = 1, SWC_PRECISION_BF16X3 = 2 };
 enum { SWC_DTYPE_F32 = 0, SWC_DTYPE_I32 = 1 };
 
 /* stages, for swc_workspace_bytes() */

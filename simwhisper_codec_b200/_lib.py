@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libswc.so")
 
-PRECISION = {"fp32": 0, "bf16": 1}
+PRECISION = {"fp32": 0, "bf16": 1, "bf16x3": 2}
 KCLASS = ("gemm_tcgen05", "gemm_simt_fp32", "attention", "layernorm", "dwconv7_ln", "aa_snake", "other")
 STAGE = {"mel": 0, "encoder": 1, "downsample": 2, "quantizer": 3, "upsample": 4, "decoder": 5, "vocos": 6,
          "tokenize": 7, "detokenize": 8, "forward": 9}

@@ -13,7 +13,9 @@ Differences that are deliberate and documented in DESIGN.md:
     results are identical to the reference's windowing (keep-first 20 s, decode pad length T' =
     batch maximum per window index, reference model.py:275-297, 340-362).
   * `precision="bf16"` selects the tcgen05 tensor-core path (fp32 residual stream, LayerNorm,
-    softmax, iSTFT); `precision="fp32"` is the parity mode.
+    softmax, iSTFT); `precision="fp32"` is the parity mode (CUDA-core FFMA everywhere);
+    `precision="bf16x3"` is the parity mode with the dense contractions on the tensor cores as three
+    bf16 products with fp32 accumulation (fp32 activations, attention, mel and iSTFT as in "fp32").
 """
 from __future__ import annotations
 

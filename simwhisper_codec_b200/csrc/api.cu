@@ -75,7 +75,9 @@ size_t dry_size(const swc_model* mm, Fn fn) {
   c.m = &mm->m;
   c.dry = true;
   fn(c);
-  return c.ws.peak + 256;
+  // bf16x3 mode: every tensor-core GEMM splits its fp32 operand into bf16 planes of the same byte size on top of whatever is
+  // live at that point; the operand is itself one allocation of this pass, so the largest one bounds the extra space
+  return c.ws.peak + 256 + (mm->m.x3() ? c.ws.largest + 512 : 0);
 }
 
 // ---- stage bodies shared by the real call and the dry sizing -------------------------------------
@@ -179,7 +181,7 @@ const char* swc_last_error(void) { return swc::g_err; }
 
 int swc_model_create(swc_model** out, int precision) {
   SWC_REQUIRE(out != nullptr, "null output pointer");
-  SWC_REQUIRE(precision == SWC_PRECISION_FP32 || precision == SWC_PRECISION_BF16, "unknown precision %d", precision);
+  SWC_REQUIRE(precision == SWC_PRECISION_FP32 || precision == SWC_PRECISION_BF16 || precision == SWC_PRECISION_BF16X3, "unknown precision %d", precision);
   *out = new swc_model();
   (*out)->m.precision = precision;
   return 0;

@@ -13,7 +13,7 @@ namespace swc {
 
 enum EpiKind { EPI_STORE = 0, EPI_POWER = 1, EPI_LOGMEL = 2, EPI_FSQ = 3, EPI_HEAD = 4 };
 
-constexpr int kMaxTaps = 8;
+constexpr int kMaxTaps = 24;     // 7-tap convolutions x 3 split-bf16 products
 
 struct FsqConst {        // per-dimension constants of one 4-dim FSQ group (reference quantizer.py:129-179)
   float scale[4];        // (L-1)/2 * (1-eps)
@@ -60,6 +60,7 @@ struct GemmDesc {
   int tap_col[kMaxTaps];
   int tap_k;                // multiple of 16 (SIMT) / 64 (tcgen05)
   const void* W;            // [N_pad, K] row-major, K = n_taps * tap_k
+  const void* W3;           // bf16x3 mode: [N_pad, 3K] bf16 planes (hi | lo | hi), else null
   int N;                    // logical output columns
   int w_rows;               // rows present in W (>= N)
   EpiParams epi;

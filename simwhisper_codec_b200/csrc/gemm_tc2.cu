@@ -404,6 +404,7 @@ int dispatch2(const GemmDesc& d, int out_type, int num_sms, cudaStream_t s) {
       if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, EW, 0, false, false, float>(d, num_sms, s);
       if (act == 0 && gamma) return launch2<CG, STAGES, NBUF, EW, 0, true, false, float>(d, num_sms, s);
       if (act == 2 && !gamma) return launch2<CG, STAGES, NBUF, EW, 2, false, false, float>(d, num_sms, s);
+      if (act == 1 && !gamma) return launch2<CG, STAGES, NBUF, EW, 1, false, false, float>(d, num_sms, s);   // exact erf (bf16x3 mode)
     }
   } else if (!reduce) {
     if (act == 0 && !gamma) return launch2<CG, STAGES, NBUF, EW, 0, false, false, bf16>(d, num_sms, s);
@@ -423,7 +424,7 @@ bool gemm_tc2_eligible(const GemmDesc& d) {
   if (e.residual && (e.residual != e.out || e.act != 0 || e.res_row_stride != e.out_row_stride * e.out_row_mul ||
                      e.out_row_off != 0 || (d.nb > 1 && e.res_batch_stride != e.out_batch_stride)))
     return false;
-  return e.out2 == nullptr && (e.act == 0 || e.act == 2) && d.N >= 256 && d.N % 8 == 0 &&
+  return e.out2 == nullptr && (e.act == 0 || e.act == 2 || (e.act == 1 && !e.residual)) && d.N >= 256 && d.N % 8 == 0 &&
          d.tap_k % BK == 0 && ((uintptr_t)e.out & 15) == 0;
 }
 

@@ -687,6 +687,42 @@ int istft_ola(const float* frames, const float* win_sq, int nb, int T, float* wa
 }
 
 // ================================================================================================
+// bf16x3 mode: split an fp32 GEMM operand into two bf16 planes (x = hi + lo up to 2^-17 relative)
+// ================================================================================================
+__global__ void __launch_bounds__(256) split_bf16_planes_kernel(const float* __restrict__ in, long long row_stride, long long batch_stride,
+                                                                int rows, int cols8, bf16* __restrict__ planes, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % cols8);
+  const long long br = i / cols8;
+  const int r = (int)(br % rows);
+  const long long b = br / rows;
+  const float* src = in + b * batch_stride + (long long)r * row_stride + c8 * 8;
+  const float4 u = *reinterpret_cast<const float4*>(src), v = *reinterpret_cast<const float4*>(src + 4);
+  const float x[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+  __align__(16) bf16 hi[8], lo[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    hi[k] = __float2bfloat16_rn(x[k]);
+    lo[k] = __float2bfloat16_rn(x[k] - __bfloat162float(hi[k]));
+  }
+  bf16* o = planes + br * (2ll * cols8 * 8) + c8 * 8;
+  *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(o + cols8 * 8) = *reinterpret_cast<const uint4*>(lo);
+}
+int split_bf16_planes(const float* in, long long row_stride, long long batch_stride, int nb, int rows, int cols, bf16* planes,
+                      cudaStream_t s) {
+  SWC_REQUIRE(cols % 8 == 0 && row_stride % 4 == 0 && batch_stride % 4 == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)planes & 15) == 0,
+              "split_bf16_planes: cols %d / strides must be multiples of 8 / 4 elements and the buffers 16-byte aligned", cols);
+  const long long total = (long long)nb * rows * (cols / 8);
+  if (total == 0) return 0;
+  ProfScope ps(KC_MISC, s);
+  split_bf16_planes_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, s>>>(in, row_stride, batch_stride, rows, cols / 8, planes, total);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================
 // ragged pack / unpack of token rows (float4 / 8-byte granules; C is a multiple of 8)
 // ================================================================================================
 __global__ void pack_rows_kernel(const float* __restrict__ padded, float* __restrict__ packed, const __grid_constant__ RaggedTable tab,

@@ -47,6 +47,11 @@ int istft_ola(const float* frames, const float* win_sq /*[640]*/, int nb, int T,
 
 // ---- ragged (packed valid tokens) transformer path: per-item token counts known on the host --------------------
 constexpr int kMaxRagged = 128;
+// bf16x3 mode: fp32 rows (nb, rows, cols; row / batch strides in elements) -> bf16 planes (nb, rows, 2 cols) = (hi | lo),
+// hi = bf16(x), lo = bf16(x - hi).  cols % 8 == 0.
+int split_bf16_planes(const float* in, long long row_stride, long long batch_stride, int nb, int rows, int cols, bf16* planes,
+                      cudaStream_t s);
+
 struct RaggedTable {          // passed by value to kernels (1 KB)
   int nb = 0;
   int t_max = 0;              // longest item

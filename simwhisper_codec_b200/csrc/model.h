@@ -25,6 +25,7 @@ struct Packed {
 
 struct LinearW {               // W [w_rows, K] row-major + optional bias[N]
   const void* w = nullptr;
+  const void* w3 = nullptr;    // bf16x3 mode: [w_rows, 3K] bf16 = (hi | lo | hi) planes of the fp32 weight, else null
   const float* bias = nullptr;
   int N = 0, w_rows = 0, K = 0;
 };
@@ -74,7 +75,9 @@ struct Model {
   const void* w_dft6 = nullptr;    // [416][6*448] split operand (act dtype) for the tensor-core DFT
   const void* w_idft3 = nullptr;   // [n_fft][3*NP] split operand (act dtype) for the tensor-core iDFT
 
-  int act_type() const { return precision; }   // 0 fp32, 1 bf16
+  int act_type() const { return precision == 1 ? 1 : 0; }   // activation storage: 0 fp32, 1 bf16
+  bool x3() const { return precision == 2; }                // fp32 activations, dense contractions as 3-product split-bf16 tcgen05 GEMMs
+  std::vector<void*> extra_allocs;                          // device buffers outside the slab (w3 planes)
 };
 
 int pack_model(Model& m);       // host only

@@ -413,7 +413,7 @@ int upload_model(Model& m, int device) {
       SWC_CHECK_CUDA(cudaMemcpy(p.dev, p.host.data(), p.host.size() * 4, cudaMemcpyHostToDevice));
       off += (p.host.size() * 4 + 255) / 256 * 256;
     }
-    std::vector<float>().swap(p.host);
+    if (!(m.x3() && p.as_act_type)) std::vector<float>().swap(p.host);     // bf16x3: L() below still needs the fp32 rows
   }
   m.raw.clear();
 
@@ -423,6 +423,31 @@ int upload_model(Model& m, int device) {
     l.w = m.tab.at(n + ".w").dev;
     l.bias = bias ? F(n + ".b") : nullptr;
     l.N = N; l.w_rows = rows; l.K = K;
+    if (m.x3()) {      // split every weight row into bf16 planes: (hi | lo | hi), the operand of the three-product GEMM
+      Packed& pw = m.tab.at(n + ".w");
+      if ((long long)pw.host.size() == (long long)rows * K) {
+        std::vector<uint16_t> w3((size_t)rows * 3 * K);
+        for (int r = 0; r < rows; ++r) {
+          for (int k = 0; k < K; ++k) {
+            const float v = pw.host[(size_t)r * K + k];
+            const uint16_t hi = f32_to_bf16_rn(v);
+            uint32_t hb = (uint32_t)hi << 16;
+            float hf;
+            std::memcpy(&hf, &hb, 4);
+            const uint16_t lo = f32_to_bf16_rn(v - hf);
+            uint16_t* o = w3.data() + (size_t)r * 3 * K;
+            o[k] = hi; o[K + k] = lo; o[2 * K + k] = hi;
+          }
+        }
+        void* dev = nullptr;
+        if (cudaMalloc(&dev, w3.size() * 2) == cudaSuccess &&
+            cudaMemcpy(dev, w3.data(), w3.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess) {
+          m.extra_allocs.push_back(dev);
+          l.w3 = dev;
+        }
+      }
+      std::vector<float>().swap(pw.host);
+    }
     return l;
   };
   const int D = m.d_model, MP = m.mel_pitch, H = m.hidden, V = m.voc_dim, I = m.voc_inter;
@@ -481,6 +506,7 @@ int upload_model(Model& m, int device) {
   m.w_idft3 = m.tab.count("voc.idft.w3") ? m.tab["voc.idft.w3"].dev : nullptr;
   m.w_dft = F("mel.dft.w"); m.w_melfb = F("mel.fb.w");
   m.w_dft6 = m.tab.count("mel.dft.w6") ? m.tab["mel.dft.w6"].dev : nullptr;
+  for (auto& kv : m.tab) std::vector<float>().swap(kv.second.host);
   m.uploaded = true;
   (void)g_slab_unused;
   return 0;
@@ -489,6 +515,8 @@ int upload_model(Model& m, int device) {
 void free_model(Model& m) {
   auto it = m.tab.find("__slab__");
   if (it != m.tab.end() && it->second.dev) cudaFree(it->second.dev);
+  for (void* p : m.extra_allocs) cudaFree(p);
+  m.extra_allocs.clear();
   m.tab.clear();
   m.raw.clear();
   m.uploaded = false;

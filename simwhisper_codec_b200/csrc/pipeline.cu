@@ -35,7 +35,7 @@ GemmDesc base_desc(const void* A, long long a_row_stride, long long a_batch_stri
   d.A = A; d.a_row_stride = a_row_stride; d.a_batch_stride = a_batch_stride; d.a_rows = a_rows; d.a_cols = a_cols;
   d.m_rows = m_rows; d.nb = nb;
   d.n_taps = 1; d.tap_row[0] = 0; d.tap_col[0] = 0; d.tap_k = w.K;
-  d.W = w.w; d.N = w.N; d.w_rows = w.w_rows;
+  d.W = w.w; d.W3 = w.w3; d.N = w.N; d.w_rows = w.w_rows;
   d.epi.bias = w.bias;
   d.epi.out_row_mul = 1; d.epi.out_row_off = 0;
   d.epi.nb = nb;
@@ -46,8 +46,36 @@ void set_out(GemmDesc& d, void* out, long long row_stride, long long batch_strid
   d.epi.out = out; d.epi.out_row_stride = row_stride; d.epi.out_batch_stride = batch_stride;
 }
 
-// dispatch on the model precision: bf16 operands go to the tcgen05 kernel, fp32 to the SIMT kernel
+// dispatch on the model precision: bf16 operands go to the tcgen05 kernel, fp32 to the SIMT kernel.
+// bf16x3 mode (fp32 activations): the fp32 operand is split into two bf16 planes (hi | lo) and the contraction runs on the
+// tensor cores as three products a_hi w_hi + a_hi w_lo + a_lo w_hi with fp32 accumulation: every tap of the problem
+// becomes three taps (the A plane is a column offset, the packed weight holds the planes hi | lo | hi along K).
 int run_gemm(Ctx& c, const GemmDesc& d, int kind, int a_type, int out_type) {
+  const bool x3 = c.m->x3() && a_type == 0 && !c.force_simt && d.W3 != nullptr && d.tap_k % 64 == 0 && d.a_cols % 8 == 0 &&
+                  3 * d.n_taps <= kMaxTaps && d.N % 8 == 0 && d.a_row_stride % 4 == 0 && d.a_batch_stride % 4 == 0;
+  if (x3) {
+    const size_t mark = c.ws.mark();
+    bf16* planes = (bf16*)c.ws.alloc((long long)d.nb * d.a_rows * d.a_cols * 4);
+    SWC_TRY(c.ws.check());
+    int rc = 0;
+    if (!c.dry) {
+      rc = split_bf16_planes((const float*)d.A, d.a_row_stride, d.a_batch_stride, d.nb, d.a_rows, d.a_cols, planes, c.s);
+      if (rc == 0) {
+        GemmDesc e = d;
+        e.A = planes; e.a_cols = 2 * d.a_cols; e.a_row_stride = 2ll * d.a_cols; e.a_batch_stride = 2ll * d.a_cols * d.a_rows;
+        e.W = d.W3; e.W3 = nullptr;
+        e.n_taps = 3 * d.n_taps;
+        for (int j = 0; j < 3; ++j)
+          for (int t = 0; t < d.n_taps; ++t) {
+            e.tap_row[j * d.n_taps + t] = d.tap_row[t];
+            e.tap_col[j * d.n_taps + t] = d.tap_col[t] + (j == 2 ? d.a_cols : 0);
+          }
+        rc = gemm_tc(e, kind, out_type, c.m->num_sms, c.s);
+      }
+    }
+    c.ws.release(mark);
+    return rc;
+  }
   if (c.dry) return 0;
   if (a_type == 1 && !c.force_simt) return gemm_tc(d, kind, out_type, c.m->num_sms, c.s);
   return gemm_simt(d, kind, a_type, out_type, c.s);

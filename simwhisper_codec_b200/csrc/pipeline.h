@@ -9,12 +9,13 @@ namespace swc {
 
 struct Arena {
   char* base = nullptr;
-  size_t cap = 0, off = 0, peak = 0;
+  size_t cap = 0, off = 0, peak = 0, largest = 0;   // largest: biggest single allocation (bounds any GEMM operand)
   bool overflow = false;
   void* alloc(long long bytes) {
     const size_t a = (off + 255) & ~(size_t)255;
     off = a + (size_t)bytes;
     peak = std::max(peak, off);
+    largest = std::max(largest, (size_t)bytes);
     if (!base) return nullptr;
     if (off > cap) { overflow = true; return nullptr; }
     return base + a;

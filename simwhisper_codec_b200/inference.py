@@ -29,7 +29,7 @@ def main(argv=None) -> int:
     ap.add_argument("--batch_size", type=int, default=8)
     ap.add_argument("--input_dir", type=str, default="input_wavs")
     ap.add_argument("--output_dir", type=str, default="output_wavs")
-    ap.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32", "bf16x3"])
     ap.add_argument("--codes_dir", type=str, default=None, help="also write <name>.swc code streams here")
     ap.add_argument("--random_init", action="store_true", help="deterministic random weights instead of a checkpoint")
     args = ap.parse_args(argv)

@@ -27,6 +27,13 @@ def model16(gen_params, sd_ex):
     return m
 
 
+@pytest.fixture(scope="module")
+def model_x3(gen_params, sd_ex):
+    m = AudioCodec(gen_params, precision="bf16x3")
+    m.load_state_dict(sd_ex)
+    return m
+
+
 def _cuda(a):
     return torch.from_numpy(np.asarray(a)).cuda()
 
@@ -253,3 +260,38 @@ def test_mel_bf16_mode_keeps_fp32_accuracy(model16):
     lens = torch.tensor([480000], device="cuda")
     mel16, _ = model16._mel(x[None, :].cuda(), lens)
     assert (mel16.cpu().double() - truth).abs().max().item() <= 1e-4
+
+
+def test_bf16x3_mode_meets_the_fp32_bars(model_x3, model32, sd_ex):
+    """precision="bf16x3": fp32 activations, every dense contraction on the tensor cores as a_hi w_hi + a_hi w_lo + a_lo w_hi
+    (fp32 accumulation, relative error ~2^-17).  It must meet the parity bars of the fp32 mode: indices equal to the
+    reference's up to near-tie flips < 0.1 %, mel max-abs-err <= 1e-4, waveform SNR >= 40 dB."""
+    g = load_golden("api_10s_ex.npz")
+    w = synthetic_wave(1000, 160000).cuda()
+    mel, mel_lens = model_x3._mel(w[None, :], torch.tensor([160000], device="cuda"))
+    assert np.abs(mel[0, :, :1008].cpu().numpy() - g["mel"]).max() <= 1e-4
+    r = model_x3.inference_tokenize(w[None, None, :], torch.tensor([160000], device="cuda"))
+    codes = r["codes"][:, 0, :125].cpu()
+    flips = (codes != torch.from_numpy(g["codes"])).float().mean().item()
+    print(f"bf16x3 index flip rate vs the reference (10 s, 1000 indices): {flips:.5f}")
+    assert flips <= 2e-3, flips            # 1000 indices: the rate itself is asserted on the 30 s windows below
+    wav = model_x3.decode([torch.from_numpy(g["codes"])])["syn_wav_list"][0]
+    s = snr_db(torch.from_numpy(g["wav"]), wav.cpu())
+    print(f"bf16x3 decode SNR vs the reference (same codes): {s:.1f} dB")
+    assert s >= 40.0
+    # full 30 s windows against the CPU oracle and against the fp32 mode on the same device
+    x = torch.stack([synthetic_wave(8000 + i, 480000) for i in range(8)])[:, None, :]
+    lens = torch.full((8,), 480000)
+    with torch.inference_mode():
+        ref = port.tokenize(sd_ex, x[:1], lens[:1])
+        ref_wav = port.detokenize(sd_ex, ref["codes"], ref["codes_lengths"])
+    rx = model_x3.inference_tokenize(x.cuda(), lens.cuda())
+    r32 = model32.inference_tokenize(x.cuda(), lens.cuda())
+    f_ref = (rx["codes"][:, :1].cpu() != ref["codes"]).float().mean().item()
+    f_32 = (rx["codes"] != r32["codes"]).float().mean().item()
+    print(f"bf16x3 index flips on 30 s windows: vs oracle {f_ref:.5f}, vs fp32 mode {f_32:.5f}")
+    assert f_ref < 1e-3 and f_32 < 1e-3
+    out = model_x3.inference_detokenize(ref["codes"].cuda(), ref["codes_lengths"].cuda())
+    s30 = snr_db(ref_wav["y"], out["y"].cpu())
+    print(f"bf16x3 decode SNR vs oracle (30 s): {s30:.1f} dB")
+    assert s30 >= 40.0
