@@ -205,6 +205,188 @@ __global__ void __launch_bounds__(kThreads, 2) attention_mma_kernel(const bf16* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// bf16x3 mode: the same flash attention at fp32-class accuracy.  q, k, v arrive as two bf16 planes each (x = hi + lo up to
+// 2^-17, split_bf16_planes of the fp32 qkv rows: plane row = [hi (3 H 64) | lo (3 H 64)]); every product is evaluated as
+// hi*hi + hi*lo + lo*hi with fp32 accumulation: S = Qh Kh^T + Ql Kh^T + Qh Kl^T, and the fp32 probabilities are split the
+// same way in registers for O += Ph Vh + Pl Vh + Ph Vl.  Softmax, row sums and the output stay fp32.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2) attention_mma_x3_kernel(const bf16* __restrict__ planes, float* __restrict__ out,
+                                                                       const long long* __restrict__ lens, int T, int H) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sQ = smem;                        // [hi, lo] x 128 x 128 B
+  uint8_t* sK = smem + 2 * QT * 128;         // [2 buffers][hi, lo] x 64 x 128 B
+  uint8_t* sV = sK + 4 * KT * 128;           // [2 buffers][hi, lo] x 64 x 128 B
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
+  const int D3 = 3 * H * HD, DO = H * HD, PR = 2 * D3;      // PR: plane row length
+  long long len_ll = lens ? lens[b] : T;
+  const int len = (int)(len_ll > T ? T : (len_ll < 0 ? 0 : len_ll));
+  const bf16* base = planes + (long long)b * T * PR;
+  float* obase = out + (long long)b * T * DO + h * HD;
+
+  if (q0 >= len) {   // tile of padded queries: defined zero output
+    for (int i = tid; i < QT * 16; i += kThreads) {
+      const int r = i >> 4, c = i & 15;
+      if (q0 + r < T) *reinterpret_cast<float4*>(obase + (long long)(q0 + r) * DO + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+
+  for (int i = tid; i < 2 * QT * 8; i += kThreads) {
+    const int pl = i / (QT * 8), j = i - pl * (QT * 8), r = j >> 3, c = j & 7;
+    const bool ok = q0 + r < T;
+    cp_async16(smem_u32(sQ) + pl * QT * 128 + swz(r, c), base + (long long)(ok ? q0 + r : 0) * PR + pl * D3 + h * HD + c * 8, ok);
+  }
+  auto load_kv = [&](int kt, int buf) {
+    const int k0 = kt * KT;
+    for (int i = tid; i < 2 * KT * 8; i += kThreads) {
+      const int pl = i / (KT * 8), j = i - pl * (KT * 8), r = j >> 3, c = j & 7;
+      const bool ok = k0 + r < len;           // masked keys are zero-filled (no NaN can enter P*V)
+      const bf16* src = base + (long long)(ok ? k0 + r : 0) * PR + pl * D3 + c * 8;
+      cp_async16(smem_u32(sK) + (buf * 2 + pl) * KT * 128 + swz(r, c), src + (H + h) * HD, ok);
+      cp_async16(smem_u32(sV) + (buf * 2 + pl) * KT * 128 + swz(r, c), src + (2 * H + h) * HD, ok);
+    }
+  };
+  load_kv(0, 0);
+  cp_commit();
+
+  const int n_kt = (len + KT - 1) / KT;
+  const int g = lane >> 2, tq = lane & 3;
+  const int wrow = warp * 16;
+
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  for (int kt = 0; kt < n_kt; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < n_kt) {
+      load_kv(kt + 1, buf ^ 1);
+      cp_commit();
+      cp_wait<1>();
+    } else {
+      cp_wait<0>();
+    }
+    __syncthreads();
+    const uint32_t kh = smem_u32(sK) + (buf * 2) * KT * 128, kl = kh + KT * 128;
+    const uint32_t vh = smem_u32(sV) + (buf * 2) * KT * 128, vl = vh + KT * 128;
+
+    // ---- S = Qh Kh^T + Ql Kh^T + Qh Kl^T : 16 x 64 per warp (the Q fragments are re-read per k-step: registers)
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t qh[4], ql[4];
+      {
+        const int r = wrow + (lane & 15), c = ks * 2 + (lane >> 4);
+        ldsm_x4(smem_u32(sQ) + swz(r, c), qh[0], qh[1], qh[2], qh[3]);
+        ldsm_x4(smem_u32(sQ) + QT * 128 + swz(r, c), ql[0], ql[1], ql[2], ql[3]);
+      }
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {     // pairs of 8-key tiles
+        uint32_t b0, b1, b2, b3;
+        const int r = np * 16 + ((lane >> 4) << 3) + (lane & 7);
+        const int c = ks * 2 + ((lane >> 3) & 1);
+        ldsm_x4(kl + swz(r, c), b0, b1, b2, b3);
+        mma_bf16(s[2 * np], qh, b0, b1);
+        mma_bf16(s[2 * np + 1], qh, b2, b3);
+        ldsm_x4(kh + swz(r, c), b0, b1, b2, b3);
+        mma_bf16(s[2 * np], ql, b0, b1);
+        mma_bf16(s[2 * np + 1], ql, b2, b3);
+        mma_bf16(s[2 * np], qh, b0, b1);
+        mma_bf16(s[2 * np + 1], qh, b2, b3);
+      }
+    }
+    const int k0 = kt * KT;
+    if (k0 + KT > len) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int key = k0 + nt * 8 + tq * 2;
+        if (key >= len) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+        if (key + 1 >= len) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);     // finite: key k0 < len is valid in every tile
+    const float c0 = exp2f((m0 - mn0) * kLog2e), c1 = exp2f((m1 - mn1) * kLog2e);
+    m0 = mn0; m1 = mn1;
+    const float ms0 = mn0 * kLog2e, ms1 = mn1 * kLog2e;
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {      // probabilities stay fp32 in the score registers
+      s[nt][0] = exp2f(fmaf(s[nt][0], kLog2e, -ms0)); s[nt][1] = exp2f(fmaf(s[nt][1], kLog2e, -ms0));
+      s[nt][2] = exp2f(fmaf(s[nt][2], kLog2e, -ms1)); s[nt][3] = exp2f(fmaf(s[nt][3], kLog2e, -ms1));
+      ps0 += s[nt][0] + s[nt][1];
+      ps1 += s[nt][2] + s[nt][3];
+    }
+    l0 = l0 * c0 + ps0;
+    l1 = l1 * c1 + ps1;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1; }
+    // ---- O += Ph Vh + Pl Vh + Ph Vl : k = 64 keys (4 steps), n = 64 dims (8 tiles)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {        // C fragments of key tiles 2ks, 2ks+1 -> A fragment of k-step ks
+        const float a = s[2 * ks + (e >> 1)][(e & 1) * 2], bb = s[2 * ks + (e >> 1)][(e & 1) * 2 + 1];
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(a, bb);
+        const float2 hf = __bfloat1622float2(hi);
+        ph[e] = *reinterpret_cast<const uint32_t*>(&hi);
+        pl[e] = pack_bf16(a - hf.x, bb - hf.y);
+      }
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {     // pairs of 8-dim tiles
+        uint32_t b0, b1, b2, b3;
+        const int r = ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+        const int c = dp * 2 + (lane >> 4);
+        ldsm_x4_t(vl + swz(r, c), b0, b1, b2, b3);
+        mma_bf16(o[2 * dp], ph, b0, b1);
+        mma_bf16(o[2 * dp + 1], ph, b2, b3);
+        ldsm_x4_t(vh + swz(r, c), b0, b1, b2, b3);
+        mma_bf16(o[2 * dp], pl, b0, b1);
+        mma_bf16(o[2 * dp + 1], pl, b2, b3);
+        mma_bf16(o[2 * dp], ph, b0, b1);
+        mma_bf16(o[2 * dp + 1], ph, b2, b3);
+      }
+    }
+    __syncthreads();   // everyone is done with buffer `buf` before it is refilled two iterations later
+  }
+
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const int r0 = q0 + wrow + g, r1 = r0 + 8;
+  const float i0 = (r0 < len && l0 > 0.f) ? 1.0f / l0 : 0.f;   // padded query rows -> 0
+  const float i1 = (r1 < len && l1 > 0.f) ? 1.0f / l1 : 0.f;
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt) {
+    const int d = dt * 8 + tq * 2;
+    if (r0 < T) *reinterpret_cast<float2*>(obase + (long long)r0 * DO + d) = make_float2(o[dt][0] * i0, o[dt][1] * i0);
+    if (r1 < T) *reinterpret_cast<float2*>(obase + (long long)r1 * DO + d) = make_float2(o[dt][2] * i1, o[dt][3] * i1);
+  }
+}
+
+constexpr int kSmemBytesX3 = 2 * QT * 128 + 8 * KT * 128;
 constexpr int kSmemBytes = QT * 128 + 4 * KT * 128;
 
 }  // namespace
@@ -218,6 +400,19 @@ int attention_mma(const bf16* qkv, bf16* out, const long long* lens, int nb, int
   }
   ProfScope ps(KC_ATTN, s);
   attention_mma_kernel<<<grid, kThreads, kSmemBytes, s>>>(qkv, out, lens, T, H);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int attention_mma_x3(const bf16* planes, float* out, const long long* lens, int nb, int T, int H, cudaStream_t s) {
+  dim3 grid(ceil_div(T, QT), H, nb);
+  static bool configured = false;
+  if (!configured) {
+    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesX3));
+    configured = true;
+  }
+  ProfScope ps(KC_ATTN, s);
+  attention_mma_x3_kernel<<<grid, kThreads, kSmemBytesX3, s>>>(planes, out, lens, T, H);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

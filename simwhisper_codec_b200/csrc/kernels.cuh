@@ -66,6 +66,8 @@ int unpack_rows(const void* packed, void* padded, int dtype, const RaggedTable& 
 
 // fp32 SIMT flash attention over fused qkv rows (nb*T, 3*H*64): q pre-scaled. Keys >= lens[b] masked.
 int attention_simt(const void* qkv, int type, void* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
+// bf16x3 mode: fp32-class flash attention on mma.sync over the (hi | lo) bf16 planes of the fp32 qkv rows, fp32 output
+int attention_mma_x3(const bf16* planes, float* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
 // bf16 tensor-core flash attention (mma.sync m16n8k16), same contract
 int attention_mma(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
 // bf16 flash attention on tcgen05 / TMEM / TMA (attention_tc.cu), same contract

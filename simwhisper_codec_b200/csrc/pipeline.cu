@@ -89,6 +89,17 @@ int run_attention(Ctx& c, const void* qkv, void* out, const long long* lens, int
     if (use_mma) return attention_mma((const bf16*)qkv, (bf16*)out, lens, nb, T, c.m->heads, c.s);
     return attention_tc((const bf16*)qkv, (bf16*)out, lens, nb, T, c.m->heads, c.m->num_sms, c.s);
   }
+  if (c.m->x3() && !c.force_simt) {
+    // bf16x3 mode: split the fp32 qkv rows into bf16 planes (same byte size), then the three-product mma.sync kernel
+    const int D3 = 3 * c.m->heads * 64;
+    const size_t mark = c.ws.mark();
+    bf16* planes = (bf16*)c.ws.alloc((long long)nb * T * D3 * 4);
+    SWC_TRY(c.ws.check());
+    int rc = split_bf16_planes((const float*)qkv, D3, (long long)T * D3, nb, T, D3, planes, c.s);
+    if (rc == 0) rc = attention_mma_x3(planes, (float*)out, lens, nb, T, c.m->heads, c.s);
+    c.ws.release(mark);
+    return rc;
+  }
   return attention_simt(qkv, at, out, lens, nb, T, c.m->heads, c.s);
 }
 
