@@ -282,10 +282,26 @@ def test_bf16x3_mode_meets_the_fp32_bars(model_x3, model32, sd_ex):
     # full 30 s windows against the CPU oracle and against the fp32 mode on the same device
     x = torch.stack([synthetic_wave(8000 + i, 480000) for i in range(8)])[:, None, :]
     lens = torch.full((8,), 480000)
+    trace = {}
     with torch.inference_mode():
-        ref = port.tokenize(sd_ex, x[:1], lens[:1])
+        ref = port.tokenize(sd_ex, x[:1], lens[:1], trace=trace)
         ref_wav = port.detokenize(sd_ex, ref["codes"], ref["codes_lengths"])
     rx = model_x3.inference_tokenize(x.cuda(), lens.cuda())
+    # near-tie audit: every index that differs from the oracle's sits on a rounding boundary of the FSQ grid (one of its
+    # four compressed coordinates within 5e-3 of k + 1/2) and lands on the neighbouring level of that coordinate
+    lv = torch.tensor([8, 7, 6, 6], dtype=torch.float64)
+    scale = (lv - 1) / 2 * (1 - 1e-3)
+    offs = torch.where(lv % 2 == 0, 0.5, 0.0)
+    shift = torch.tan(offs / scale)
+    base = torch.tensor([1, 8, 56, 336])
+    got = rx["codes"][:, 0].cpu()
+    for gi, ti in (got != ref["codes"][:, 0]).nonzero().tolist():
+        z = trace["latent"][0, 4 * gi:4 * gi + 4, ti].double()
+        c = scale * torch.tanh(z + shift) - offs
+        margin = ((c - torch.floor(c)) - 0.5).abs()
+        da = (got[gi, ti] // base) % lv.long() - (ref["codes"][gi, 0, ti] // base) % lv.long()
+        assert int(da.abs().sum()) == 1, (gi, ti, da.tolist())
+        assert float(margin[int(da.abs().argmax())]) < 5e-3, (gi, ti, margin.tolist())
     r32 = model32.inference_tokenize(x.cuda(), lens.cuda())
     f_ref = (rx["codes"][:, :1].cpu() != ref["codes"]).float().mean().item()
     f_32 = (rx["codes"] != r32["codes"]).float().mean().item()

@@ -85,3 +85,26 @@ def test_forward_small_emulated(emu):
     assert float(mel_dec[..., 80:].abs().max()) == 0.0
     wav = emu.vocos(mel_dec)
     assert snr_db(torch.from_numpy(g["audio"])[:, 0], wav) > 80.0
+
+
+def test_bf16x3_split_arithmetic():
+    """The operand split of the bf16x3 mode (pack.cu / split_bf16_planes): x = hi + lo up to 2^-17 |x|, and the three
+    products hi*hi + hi*lo + lo*hi with fp32 accumulation reproduce an fp32 contraction to ~1e-5 of sum |a||w|."""
+    import numpy as np
+    import torch
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(64, 768, generator=g)
+    w = torch.randn(96, 768, generator=g) * 0.05
+    def split(x):
+        hi = x.bfloat16().float()
+        lo = (x - hi).bfloat16().float()
+        return hi, lo
+    ah, al = split(a)
+    wh, wl = split(w)
+    assert float(((a - ah - al).abs() / a.abs().clamp_min(1e-30)).max()) <= 2.0 ** -16
+    ref = a.double() @ w.double().T
+    got = (ah @ wh.T + ah @ wl.T + al @ wh.T).double()
+    scale = (a.abs().double() @ w.abs().double().T)
+    assert float(((got - ref).abs() / scale).max()) < 2e-5
+    plain = (ah @ wh.T).double()                       # single bf16 product for contrast: ~2^-9
+    assert float(((plain - ref).abs() / scale).max()) > 1e-4
