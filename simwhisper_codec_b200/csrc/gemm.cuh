@@ -35,6 +35,8 @@ struct EpiParams {
   long long out_row_stride, out_batch_stride;
   int out_row_mul, out_row_off;   // output row = m * mul + off (deconv parity interleave)
   bf16* out2;               // optional second bf16 copy with the same addressing (bf16 mode)
+  int out_planes;           // bf16x3 mode: write the result as two bf16 planes (hi at column n, lo at column N + n) of a bf16
+                            // output with 2N-wide rows: the split operand of the next three-product GEMM (pair kernel only)
   // EPI_LOGMEL
   float* item_max;          // [nb], initialised to -inf
   // EPI_FSQ (N == 32)
@@ -53,6 +55,7 @@ struct GemmDesc {
   long long a_batch_stride; // elements
   int a_rows;               // valid rows per batch
   int a_cols;               // logical row width (for the tensor map)
+  int a_planes;             // bf16x3 mode: A already holds (hi | lo) bf16 planes of a_cols columns each (strides in bf16 elements)
   int m_rows;               // output rows per batch
   int nb;                   // batches
   int n_taps;

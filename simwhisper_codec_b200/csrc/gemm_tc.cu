@@ -378,7 +378,8 @@ int get_gemm_variant() {
 }
 
 int gemm_tc(const GemmDesc& d, int kind, int out_type, int num_sms, cudaStream_t s) {
-  if (kind == EPI_STORE && get_gemm_variant() > 0 && gemm_tc2_eligible(d) && !(d.epi.residual && out_type != 0) && !(d.epi.act == 1 && out_type != 0)) return gemm_tc2(d, out_type, num_sms, get_gemm_variant(), s);
+  if (kind == EPI_STORE && get_gemm_variant() > 0 && gemm_tc2_eligible(d) && !(d.epi.residual && out_type != 0) && !(d.epi.act == 1 && out_type != 0 && !d.epi.out_planes)) return gemm_tc2(d, out_type, num_sms, get_gemm_variant(), s);
+  SWC_REQUIRE(!d.epi.out_planes, "gemm_tc: a planes output is only written by the pair kernel (problem not eligible for it)");
   SWC_REQUIRE(d.tap_k % BK == 0 && d.n_taps >= 1 && d.n_taps <= kMaxTaps, "gemm_tc: tap_k=%d must be a multiple of 64 (taps=%d)", d.tap_k, d.n_taps);
   SWC_REQUIRE(d.m_rows > 0 && d.nb > 0 && d.N > 0, "gemm_tc: empty problem");
   SWC_REQUIRE(((uintptr_t)d.A & 15) == 0 && ((uintptr_t)d.W & 15) == 0, "gemm_tc: operands must be 16-byte aligned");

@@ -157,7 +157,7 @@ __device__ __forceinline__ void convert_sub(const uint32_t (&acc)[32], const flo
 // One epilogue warp's share of an output tile: its 32 TMEM lanes x kSlice accumulator columns -> bias / activation /
 // gamma -> 128B-swizzled staging boxes -> TMA store (or reduce-add).  `taddr` addresses the warp's first column of the
 // accumulator buffer; the buffer is handed back (arrive on `tempty_addr`) as soon as it is in registers.
-template <int NBUF, int EW, int ACT, bool GAMMA, bool REDUCE, typename TO>
+template <int NBUF, int EW, int ACT, bool GAMMA, bool REDUCE, typename TO, bool PLANES = false>
 __device__ __forceinline__ void epilogue_tile(const CUtensorMap* tmO, const Tc2Params& p, uint32_t taddr, uint32_t tempty_addr,
                                               uint8_t* stage_out, int& obuf, int lane, int lg, int c_base, int b, int m0, int n0) {
   constexpr int kSlice = BN / (EW / 4);
@@ -174,6 +174,51 @@ __device__ __forceinline__ void epilogue_tile(const CUtensorMap* tmO, const Tc2P
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_addr);
+    }
+    if constexpr (PLANES) {
+      // bf16x3 hand-over: the fp32 result goes out as two bf16 planes (hi | lo), one staging box each; two 64-column
+      // TMA stores per pair of chunks, at columns n and N + n of the 2N-wide output rows
+      static_assert(!PLANES || (NBUF == 2 && sizeof(TO) == 2 && !REDUCE && !GAMMA), "planes epilogue: bf16, two staging boxes");
+      if ((sub & 1) == 0) {
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+      }
+      const uint32_t box_hi = smem_u32(stage_out) + (uint32_t)lane * 128u, box_lo = box_hi + kOutBytesPerWarp;
+      const int ncol = n0 + c_base + sub * 32;
+      const float* sbc = p.bias ? p.bias + ncol : nullptr;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[8];
+        if (sbc != nullptr && ncol + 32 <= p.N) {
+          epi4<ACT, false, true>(&rr[sub & 1][8 * q], sbc + 8 * q, nullptr, true, v);
+          epi4<ACT, false, true>(&rr[sub & 1][8 * q + 4], sbc + 8 * q + 4, nullptr, true, v + 4);
+        } else {
+          epi4<ACT, false, false>(&rr[sub & 1][8 * q], sbc ? sbc + 8 * q : nullptr, nullptr, ncol + 8 * q + 4 <= p.N, v);
+          epi4<ACT, false, false>(&rr[sub & 1][8 * q + 4], sbc ? sbc + 8 * q + 4 : nullptr, nullptr, ncol + 8 * q + 8 <= p.N, v + 4);
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          const float2 hf = __bfloat1622float2(h2);
+          hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+          lo[e] = pack_bf16(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+        }
+        const uint32_t chunk = (uint32_t)((sub & 1) * 4 + q);
+        st_shared_v4(box_hi + ((chunk ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+        st_shared_v4(box_lo + ((chunk ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+      }
+      if ((sub & 1) == 1) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int col = n0 + c_base + (sub >> 1) * 64;
+          tma_store_3d(tmO, stage_out, col, m0 + lg * 32, b);
+          tma_store_3d(tmO, stage_out + kOutBytesPerWarp, p.N + col, m0 + lg * 32, b);
+          tma_store_commit();
+        }
+      }
+      continue;
     }
     const bool new_box = kF32 || (sub & 1) == 0;
     if (new_box) {                        // the staging box must have been read by its previous TMA store
@@ -202,7 +247,7 @@ __device__ __forceinline__ void epilogue_tile(const CUtensorMap* tmO, const Tc2P
   }
 }
 
-template <int CG, int STAGES, int NBUF, int EW, int ACT, bool GAMMA, bool REDUCE, typename TO>
+template <int CG, int STAGES, int NBUF, int EW, int ACT, bool GAMMA, bool REDUCE, typename TO, bool PLANES = false>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmO, const Tc2Params p) {
@@ -318,7 +363,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int n0 = (r % p.n_tiles) * BN;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<NBUF, EW, ACT, GAMMA, REDUCE, TO>(&tmO, p, tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + c_base,
+      epilogue_tile<NBUF, EW, ACT, GAMMA, REDUCE, TO, PLANES>(&tmO, p, tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + c_base,
                                                       tempty_leader[acc], stage_out, obuf, lane, lg, c_base, b, m0, n0);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -335,7 +380,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int CG, int STAGES, int NBUF, int EW, int ACT, bool GAMMA, bool REDUCE, typename TO>
+template <int CG, int STAGES, int NBUF, int EW, int ACT, bool GAMMA, bool REDUCE, typename TO, bool PLANES = false>
 int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
   using L = Smem2<CG, STAGES, NBUF, EW>;
   constexpr int out_type = sizeof(TO) == 4 ? 0 : 1;
@@ -357,7 +402,7 @@ int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
     const size_t es = sizeof(TO);
     const long long row_stride = d.epi.out_row_stride * d.epi.out_row_mul;
     const char* base = (const char*)d.epi.out + (size_t)d.epi.out_row_off * d.epi.out_row_stride * es;
-    cuuint64_t dims[3] = {(cuuint64_t)d.N, (cuuint64_t)d.m_rows, (cuuint64_t)d.nb};
+    cuuint64_t dims[3] = {(cuuint64_t)(PLANES ? 2 * d.N : d.N), (cuuint64_t)d.m_rows, (cuuint64_t)d.nb};
     cuuint64_t strides[2] = {(cuuint64_t)row_stride * es, (cuuint64_t)(d.nb > 1 ? d.epi.out_batch_stride : row_stride * d.m_rows) * es};
     cuuint32_t box[3] = {(cuuint32_t)(128 / es), 32, 1};
     SWC_TRY(make_tmap(&tmO, out_type, base, 3, dims, strides, box));
@@ -369,7 +414,7 @@ int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
   p.n_taps = d.n_taps; p.kb_per_tap = d.tap_k / BK;
   for (int i = 0; i < d.n_taps; ++i) { p.tap_row[i] = d.tap_row[i]; p.tap_col[i] = d.tap_col[i]; }
   p.bias = d.epi.bias; p.gamma = d.epi.gamma;
-  auto kern = gemm_tc2_kernel<CG, STAGES, NBUF, EW, ACT, GAMMA, REDUCE, TO>;
+  auto kern = gemm_tc2_kernel<CG, STAGES, NBUF, EW, ACT, GAMMA, REDUCE, TO, PLANES>;
   static bool configured = false;
   if (!configured) {
     SWC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -433,6 +478,12 @@ int gemm_tc2(const GemmDesc& d, int out_type, int num_sms, int variant, cudaStre
   SWC_REQUIRE(gemm_tc2_eligible(d), "gemm_tc2: problem not eligible (residual/out2/act/N)");
   SWC_REQUIRE(d.m_rows > 0 && d.nb > 0, "gemm_tc2: empty problem");
   SWC_REQUIRE(((uintptr_t)d.A & 15) == 0 && ((uintptr_t)d.W & 15) == 0, "gemm_tc2: operands must be 16-byte aligned");
+  if (d.epi.out_planes) {     // bf16x3 hand-over of an exact-erf GELU (or plain) result to the next three-product GEMM
+    SWC_REQUIRE(out_type == 1 && d.N % 64 == 0 && !d.epi.gamma && !d.epi.residual && (d.epi.act == 0 || d.epi.act == 1),
+                "gemm_tc2: planes output needs a bf16 result, N %% 64 == 0 and no gamma / residual");
+    if (d.epi.act == 1) return launch2<2, 5, 2, 8, 1, false, false, bf16, true>(d, num_sms, s);
+    return launch2<2, 5, 2, 8, 0, false, false, bf16, true>(d, num_sms, s);
+  }
   if (variant == 1) return dispatch2<1, 4, 1, 8>(d, out_type, num_sms, s);
   if (variant == 3) return dispatch2<2, 5, 1, 16>(d, out_type, num_sms, s);  // 16 epilogue warps (64 columns each), 5-stage ring
   // Short K with a bf16 result (pwconv1, to_stacked: 8 K slabs per tile, two staging boxes per warp and tile): the tile

@@ -46,6 +46,13 @@ void set_out(GemmDesc& d, void* out, long long row_stride, long long batch_strid
   d.epi.out = out; d.epi.out_row_stride = row_stride; d.epi.out_batch_stride = batch_stride;
 }
 
+// bf16x3 mode: may the producer GEMM `a` write its result as bf16 planes for the consumer GEMM `b`?  Both must take the
+// three-product path and the producer must run on the pair kernel (the only one with the planes epilogue).
+bool x3_planes(const Ctx& c, const LinearW& a, const LinearW& b) {
+  return c.m->x3() && !c.force_simt && !c.dry && a.w3 != nullptr && b.w3 != nullptr && get_gemm_variant() == 2 && a.N % 64 == 0 &&
+         a.N >= 256 && a.K % 64 == 0 && b.K == a.N;
+}
+
 // dispatch on the model precision: bf16 operands go to the tcgen05 kernel, fp32 to the SIMT kernel.
 // bf16x3 mode (fp32 activations): the fp32 operand is split into two bf16 planes (hi | lo) and the contraction runs on the
 // tensor cores as three products a_hi w_hi + a_hi w_lo + a_lo w_hi with fp32 accumulation: every tap of the problem
@@ -53,16 +60,19 @@ void set_out(GemmDesc& d, void* out, long long row_stride, long long batch_strid
 int run_gemm(Ctx& c, const GemmDesc& d, int kind, int a_type, int out_type) {
   const bool x3 = c.m->x3() && a_type == 0 && !c.force_simt && d.W3 != nullptr && d.tap_k % 64 == 0 && d.a_cols % 8 == 0 &&
                   3 * d.n_taps <= kMaxTaps && d.N % 8 == 0 && d.a_row_stride % 4 == 0 && d.a_batch_stride % 4 == 0;
+  if (!c.dry) SWC_REQUIRE(x3 || (!d.a_planes && !d.epi.out_planes), "run_gemm: plane operands need the three-product path");
   if (x3) {
     const size_t mark = c.ws.mark();
-    bf16* planes = (bf16*)c.ws.alloc((long long)d.nb * d.a_rows * d.a_cols * 4);
+    bf16* planes = d.a_planes ? (bf16*)d.A : (bf16*)c.ws.alloc((long long)d.nb * d.a_rows * d.a_cols * 4);
     SWC_TRY(c.ws.check());
     int rc = 0;
     if (!c.dry) {
-      rc = split_bf16_planes((const float*)d.A, d.a_row_stride, d.a_batch_stride, d.nb, d.a_rows, d.a_cols, planes, c.s);
+      if (!d.a_planes)
+        rc = split_bf16_planes((const float*)d.A, d.a_row_stride, d.a_batch_stride, d.nb, d.a_rows, d.a_cols, planes, c.s);
       if (rc == 0) {
         GemmDesc e = d;
-        e.A = planes; e.a_cols = 2 * d.a_cols; e.a_row_stride = 2ll * d.a_cols; e.a_batch_stride = 2ll * d.a_cols * d.a_rows;
+        e.A = planes; e.a_cols = 2 * d.a_cols; e.a_planes = 0;
+        if (!d.a_planes) { e.a_row_stride = 2ll * d.a_cols; e.a_batch_stride = 2ll * d.a_cols * d.a_rows; }
         e.W = d.W3; e.W3 = nullptr;
         e.n_taps = 3 * d.n_taps;
         for (int j = 0; j < 3; ++j)
@@ -81,7 +91,7 @@ int run_gemm(Ctx& c, const GemmDesc& d, int kind, int a_type, int out_type) {
   return gemm_simt(d, kind, a_type, out_type, c.s);
 }
 
-int run_attention(Ctx& c, const void* qkv, void* out, const long long* lens, int nb, int T) {
+int run_attention(Ctx& c, const void* qkv, void* out, const long long* lens, int nb, int T, bool qkv_planes = false) {
   if (c.dry) return 0;
   const int at = c.m->act_type();
   if (at == 1 && !c.force_simt) {
@@ -91,6 +101,8 @@ int run_attention(Ctx& c, const void* qkv, void* out, const long long* lens, int
   }
   if (c.m->x3() && !c.force_simt) {
     // bf16x3 mode: split the fp32 qkv rows into bf16 planes (same byte size), then the three-product mma.sync kernel
+    // (the qkv GEMM hands the planes over directly when it ran on the pair kernel: qkv_planes)
+    if (qkv_planes) return attention_mma_x3((const bf16*)qkv, (float*)out, lens, nb, T, c.m->heads, c.s);
     const int D3 = 3 * c.m->heads * 64;
     const size_t mark = c.ws.mark();
     bf16* planes = (bf16*)c.ws.alloc((long long)nb * T * D3 * 4);
@@ -128,14 +140,17 @@ int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const
   SWC_TRY(c.ws.check());
   for (size_t li = 0; li < layers.size() && !c.dry; ++li) {
     const LayerW& L = layers[li];
+    // bf16x3 mode: the qkv GEMM writes the (hi | lo) planes the three-product attention kernel reads
+    const bool qkv_planes = c.m->x3() && !c.force_simt && L.qkv.w3 != nullptr && get_gemm_variant() == 2 && !rag;
     SWC_TRY(layernorm(h, nullptr, nullptr, xn, at, L.ln1_g, L.ln1_b, 1e-5f, nb, T, T, D, nullptr, c.s));
     {
       GemmDesc d = base_desc(xn, D, 0, (int)rows, D, (int)rows, 1, L.qkv);
-      set_out(d, qkv, 3 * D, 0);
-      SWC_TRY(run_gemm(c, d, EPI_STORE, at, at));
+      set_out(d, qkv, qkv_planes ? 6 * D : 3 * D, 0);
+      d.epi.out_planes = qkv_planes;
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, qkv_planes ? 1 : at));
     }
     if (rag) SWC_TRY(attention_tc_ragged((const bf16*)qkv, (bf16*)ao, *rag, m.heads, m.num_sms, c.s));
-    else SWC_TRY(run_attention(c, qkv, ao, lens, nb, T));
+    else SWC_TRY(run_attention(c, qkv, ao, lens, nb, T, qkv_planes));
     {
       GemmDesc d = base_desc(ao, D, 0, (int)rows, D, (int)rows, 1, L.out);
       set_out(d, h, D, 0);
@@ -143,14 +158,19 @@ int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
     }
     SWC_TRY(layernorm(h, nullptr, nullptr, xn, at, L.ln2_g, L.ln2_b, 1e-5f, nb, T, T, D, nullptr, c.s));
+    // bf16x3 mode: fc1 hands its GELU output to fc2 as the two bf16 planes fc2's three-product GEMM reads (same bytes as
+    // the fp32 hidden, no separate split pass over the widest operand of the layer)
+    const bool planes = x3_planes(c, L.fc1, L.fc2);
     {
       GemmDesc d = base_desc(xn, D, 0, (int)rows, D, (int)rows, 1, L.fc1);
-      set_out(d, ff, m.ffn, 0);
+      set_out(d, ff, planes ? 2 * m.ffn : m.ffn, 0);
       d.epi.act = gelu;
-      SWC_TRY(run_gemm(c, d, EPI_STORE, at, at));
+      d.epi.out_planes = planes;
+      SWC_TRY(run_gemm(c, d, EPI_STORE, at, planes ? 1 : at));
     }
     {
-      GemmDesc d = base_desc(ff, m.ffn, 0, (int)rows, m.ffn, (int)rows, 1, L.fc2);
+      GemmDesc d = base_desc(ff, planes ? 2 * m.ffn : m.ffn, 0, (int)rows, m.ffn, (int)rows, 1, L.fc2);
+      d.a_planes = planes;
       set_out(d, h, D, 0);
       d.epi.residual = h; d.epi.res_row_stride = D;
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
@@ -390,14 +410,17 @@ int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav, int Tv_in, 
     SWC_TRY(layernorm(e, nullptr, nullptr, x, 0, m.voc_norm_g, m.voc_norm_b, 1e-6f, nb, Tv, Tv, V, nullptr, c.s));
     for (const VocosBlockW& B : m.voc_blocks) {
       SWC_TRY(dwconv7_ln(x, nullptr, nullptr, B.dw_w, B.dw_b, B.ln_g, B.ln_b, 1e-6f, y, at, nb, Tv, V, c.s));
+      const bool planes = x3_planes(c, B.pw1, B.pw2);      // bf16x3 mode: the 4096-wide hidden goes to pwconv2 as bf16 planes
       {
         GemmDesc d = base_desc(y, V, 0, (int)rows, V, (int)rows, 1, B.pw1);
-        set_out(d, g, I, 0);
+        set_out(d, g, planes ? 2 * I : I, 0);
         d.epi.act = at == 1 ? 2 : 1;
-        SWC_TRY(run_gemm(c, d, EPI_STORE, at, at));
+        d.epi.out_planes = planes;
+        SWC_TRY(run_gemm(c, d, EPI_STORE, at, planes ? 1 : at));
       }
       {
-        GemmDesc d = base_desc(g, I, 0, (int)rows, I, (int)rows, 1, B.pw2);
+        GemmDesc d = base_desc(g, planes ? 2 * I : I, 0, (int)rows, I, (int)rows, 1, B.pw2);
+        d.a_planes = planes;
         set_out(d, x, V, 0);
         d.epi.gamma = B.gamma;
         d.epi.residual = x; d.epi.res_row_stride = V;
