@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Phase timeline of one persistent CTA of the tcgen05 attention kernel (clock64 stamps of the first softmax warp of query
-tile 0): A item decoded | per key block: B S ready, C P handed over | D last P V done | E item stored."""
+tile 0): A item decoded | per key block: B S ready, C P handed over | D last P V done | E item stored.
+`--fine` for a library built with -DSWC_ATTN_FINE_TRACE (four more stamps per key block; they perturb the kernel by ~20 %)."""
 import ctypes as C
 import os
 import sys
@@ -38,22 +39,31 @@ def main():
     t = buf[:4096]
     t = t[t > 0]
     n_kt = 12
-    per = 1 + 6 * n_kt + 2
+    # the default build stamps B (S ready) and C (P handed over) per key block; a library built with
+    # -DSWC_ATTN_FINE_TRACE adds B1 (S in registers), B2 (row maximum known), B3 (exponentials done), B4 (previous P V done)
+    fine = "--fine" in sys.argv
+    k = 6 if fine else 2
+    per = 1 + k * n_kt + 2
     items = len(t) // per
     t = t[: items * per].reshape(items, per)
     A, D, E = t[:, 0], t[:, -2], t[:, -1]
-    blk = t[:, 1:1 + 6 * n_kt].reshape(items, n_kt, 6)     # B, B1, B2, B3, B4, C per key block
+    blk = t[:, 1:1 + k * n_kt].reshape(items, n_kt, k)
+    if not fine:      # B, C only: fill the intermediate stamps with B so that their differences read 0
+        blk = np.stack([blk[:, :, 0]] * 5 + [blk[:, :, 1]], axis=2)
     B_, C_ = blk[:, :, 0], blk[:, :, 5]
     print(f"{items} items traced; cycles (median over items 2..):")
     sl = slice(2, None)
     med = lambda a: int(np.median(a[sl]))
     print("  item period (A -> next A)        ", med(np.diff(A)))
     print("  A -> B0 (first S ready)          ", med(B_[:, 0] - A))
-    print("  B -> B1 (S: TMEM -> registers)   ", med(blk[:, :, 1] - blk[:, :, 0]))
-    print("  B1 -> B2 (row max + exchange)    ", med(blk[:, :, 2] - blk[:, :, 1]))
-    print("  B2 -> B3 (exponentials)          ", med(blk[:, :, 3] - blk[:, :, 2]))
-    print("  B3 -> B4 (wait previous P V)     ", med(blk[:, 1:, 4] - blk[:, 1:, 3]))
-    print("  B4 -> C (P -> TMEM, hand over)   ", med(blk[:, :, 5] - blk[:, :, 4]))
+    if fine:
+        print("  B -> B1 (S: TMEM -> registers)   ", med(blk[:, :, 1] - blk[:, :, 0]))
+        print("  B1 -> B2 (row max + exchange)    ", med(blk[:, :, 2] - blk[:, :, 1]))
+        print("  B2 -> B3 (exponentials)          ", med(blk[:, :, 3] - blk[:, :, 2]))
+        print("  B3 -> B4 (wait previous P V)     ", med(blk[:, 1:, 4] - blk[:, 1:, 3]))
+        print("  B4 -> C (P -> TMEM, hand over)   ", med(blk[:, :, 5] - blk[:, :, 4]))
+    else:
+        print("  B_j -> C_j (softmax of a block)  ", med(C_ - B_))
     print("  C_j -> B_j+1 (wait for next S)   ", med(B_[:, 1:] - C_[:, :-1]))
     print("  C_last -> D (last P V)           ", med(D - C_[:, -1]))
     print("  D -> E (O read, normalise, store)", med(E - D))
