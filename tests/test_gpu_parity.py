@@ -93,8 +93,11 @@ def test_tokenize_detokenize_10s_fp32(model32):
     assert snr_db(torch.from_numpy(g["wav"]), wav.cpu()) >= 40.0
 
 
-def test_api_windows_fp32(model32):
-    """variable-length batch incl. a 50 s item: window flattening must reproduce the reference stitching."""
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
+def test_api_windows_fp32(mode, model32, model_x3):
+    """variable-length batch incl. a 50 s item: window flattening must reproduce the reference stitching (both parity-grade
+    precisions: CUDA-core fp32 and the three-product tensor-core mode)."""
+    model32 = model32 if mode == "fp32" else model_x3
     g = load_golden("api_batch_ex.npz")
     lens = g["lens"].tolist()
     wavs = [synthetic_wave(2000 + i, n) for i, n in enumerate(lens)]
