@@ -314,3 +314,29 @@ def test_bf16x3_mode_meets_the_fp32_bars(model_x3, model32, sd_ex):
     s30 = snr_db(ref_wav["y"], out["y"].cpu())
     print(f"bf16x3 decode SNR vs oracle (30 s): {s30:.1f} dB")
     assert s30 >= 40.0
+
+
+def test_api_edge_cases_fp32(model32, sd_ex):
+    """Ragged and degenerate inputs through encode()/decode() against the oracle's restatement of the reference API:
+    items shorter than one code frame (0 codes), exactly one frame, one sample short of two frames, mixed short items in
+    one batch (T' = the batch maximum), and batches whose every item is empty."""
+    lens = [100, 1280, 2559, 35000, 12800]
+    wavs = [synthetic_wave(9000 + i, n) for i, n in enumerate(lens)]
+    with torch.inference_mode():
+        ref_codes = port.encode(sd_ex, wavs)
+        ref_wavs = port.decode(sd_ex, ref_codes)
+    codes = model32.encode(wavs)["codes_list"]
+    assert [tuple(c.shape) for c in codes] == [(8, n // 1280) for n in lens] == [tuple(c.shape) for c in ref_codes]
+    total = sum(c.numel() for c in codes)
+    flips = sum((c.cpu().long() != r.long()).sum().item() for c, r in zip(codes, ref_codes))
+    assert flips / total < 1e-3, (flips, total)
+    out = model32.decode([r.long() for r in ref_codes])["syn_wav_list"]
+    assert [len(w) for w in out] == [1280 * (n // 1280) for n in lens] == [len(w) for w in ref_wavs]
+    for w, r in zip(out, ref_wavs):
+        if len(r):
+            assert snr_db(r, w.cpu()) >= 40.0
+    # nothing but empty items
+    e = model32.encode([synthetic_wave(1, 100), synthetic_wave(2, 0)])["codes_list"]
+    assert [tuple(c.shape) for c in e] == [(8, 0), (8, 0)]
+    d = model32.decode([torch.zeros(8, 0, dtype=torch.long), torch.zeros(8, 0, dtype=torch.long)])["syn_wav_list"]
+    assert [len(w) for w in d] == [0, 0]
