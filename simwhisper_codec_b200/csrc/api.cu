@@ -353,7 +353,7 @@ int swc_tokenize_ragged(const swc_model* m, const float* wav, int64_t wav_stride
                         void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();
   RaggedTable tab;
-  if (m->m.act_type() == 1 && build_ragged(tab, host_lengths, batch, 0, wav_cols < 480000 ? wav_cols : 480000)) c.rag = &tab;
+  if ((m->m.act_type() == 1 || m->m.x3()) && build_ragged(tab, host_lengths, batch, 0, wav_cols < 480000 ? wav_cols : 480000)) c.rag = &tab;
   return tokenize_chain(c, wav, wav_stride, wav_cols, (const long long*)lengths, batch, codes, zq_cf, (long long*)codes_lens);
 }
 
@@ -363,7 +363,7 @@ int swc_detokenize_ragged(const swc_model* m, const void* codes, int codes_are_i
   SWC_ENTER();
   SWC_REQUIRE(code_frames > 0, "detokenize: no code frames");
   RaggedTable tab;
-  if (m->m.act_type() == 1 && build_ragged(tab, host_lens, batch, 1, code_frames)) c.rag = &tab;
+  if ((m->m.act_type() == 1 || m->m.x3()) && build_ragged(tab, host_lens, batch, 1, code_frames)) c.rag = &tab;
   return stage_detokenize(c, codes, codes_are_int64, (const long long*)lens, batch, code_frames, wav, (long long*)out_lens);
 }
 

@@ -211,8 +211,10 @@ __global__ void __launch_bounds__(kThreads, 2) attention_mma_kernel(const bf16* 
 // hi*hi + hi*lo + lo*hi with fp32 accumulation: S = Qh Kh^T + Ql Kh^T + Qh Kl^T, and the fp32 probabilities are split the
 // same way in registers for O += Ph Vh + Pl Vh + Ph Vl.  Softmax, row sums and the output stay fp32.
 // ------------------------------------------------------------------------------------------------
+template <bool RAGGED>
 __global__ void __launch_bounds__(kThreads, 2) attention_mma_x3_kernel(const bf16* __restrict__ planes, float* __restrict__ out,
-                                                                       const long long* __restrict__ lens, int T, int H) {
+                                                                       const long long* __restrict__ lens, int T, int H,
+                                                                       const __grid_constant__ RaggedTable tab) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sQ = smem;                        // [hi, lo] x 128 x 128 B
   uint8_t* sK = smem + 2 * QT * 128;         // [2 buffers][hi, lo] x 64 x 128 B
@@ -221,12 +223,23 @@ __global__ void __launch_bounds__(kThreads, 2) attention_mma_x3_kernel(const bf1
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
   const int D3 = 3 * H * HD, DO = H * HD, PR = 2 * D3;      // PR: plane row length
-  long long len_ll = lens ? lens[b] : T;
-  const int len = (int)(len_ll > T ? T : (len_ll < 0 ? 0 : len_ll));
-  const bf16* base = planes + (long long)b * T * PR;
-  float* obase = out + (long long)b * T * DO + h * HD;
+  // RAGGED: rows are packed (item b = rows [off[b], off[b] + len[b])); rows >= len do not exist and nothing is written for them
+  int len;
+  long long row0;
+  if constexpr (RAGGED) {
+    len = tab.len[b];
+    row0 = tab.off[b];
+  } else {
+    long long len_ll = lens ? lens[b] : T;
+    len = (int)(len_ll > T ? T : (len_ll < 0 ? 0 : len_ll));
+    row0 = (long long)b * T;
+  }
+  const int Tq = RAGGED ? len : T;           // query rows that exist
+  const bf16* base = planes + row0 * PR;
+  float* obase = out + row0 * DO + h * HD;
 
   if (q0 >= len) {   // tile of padded queries: defined zero output
+    if constexpr (RAGGED) return;
     for (int i = tid; i < QT * 16; i += kThreads) {
       const int r = i >> 4, c = i & 15;
       if (q0 + r < T) *reinterpret_cast<float4*>(obase + (long long)(q0 + r) * DO + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -236,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_mma_x3_kernel(const bf1
 
   for (int i = tid; i < 2 * QT * 8; i += kThreads) {
     const int pl = i / (QT * 8), j = i - pl * (QT * 8), r = j >> 3, c = j & 7;
-    const bool ok = q0 + r < T;
+    const bool ok = q0 + r < Tq;
     cp_async16(smem_u32(sQ) + pl * QT * 128 + swz(r, c), base + (long long)(ok ? q0 + r : 0) * PR + pl * D3 + h * HD + c * 8, ok);
   }
   auto load_kv = [&](int kt, int buf) {
@@ -381,8 +394,8 @@ __global__ void __launch_bounds__(kThreads, 2) attention_mma_x3_kernel(const bf1
 #pragma unroll
   for (int dt = 0; dt < 8; ++dt) {
     const int d = dt * 8 + tq * 2;
-    if (r0 < T) *reinterpret_cast<float2*>(obase + (long long)r0 * DO + d) = make_float2(o[dt][0] * i0, o[dt][1] * i0);
-    if (r1 < T) *reinterpret_cast<float2*>(obase + (long long)r1 * DO + d) = make_float2(o[dt][2] * i1, o[dt][3] * i1);
+    if (r0 < Tq) *reinterpret_cast<float2*>(obase + (long long)r0 * DO + d) = make_float2(o[dt][0] * i0, o[dt][1] * i0);
+    if (r1 < Tq) *reinterpret_cast<float2*>(obase + (long long)r1 * DO + d) = make_float2(o[dt][2] * i1, o[dt][3] * i1);
   }
 }
 
@@ -408,11 +421,25 @@ int attention_mma_x3(const bf16* planes, float* out, const long long* lens, int 
   dim3 grid(ceil_div(T, QT), H, nb);
   static bool configured = false;
   if (!configured) {
-    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesX3));
+    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesX3));
     configured = true;
   }
   ProfScope ps(KC_ATTN, s);
-  attention_mma_x3_kernel<<<grid, kThreads, kSmemBytesX3, s>>>(planes, out, lens, T, H);
+  attention_mma_x3_kernel<false><<<grid, kThreads, kSmemBytesX3, s>>>(planes, out, lens, T, H, RaggedTable{});
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int attention_mma_x3_ragged(const bf16* planes, float* out, const RaggedTable& tab, int H, cudaStream_t s) {
+  SWC_REQUIRE(tab.nb > 0 && tab.nb <= kMaxRagged && tab.total > 0 && tab.t_max > 0, "attention_mma_x3_ragged: bad table");
+  dim3 grid(ceil_div(tab.t_max, QT), H, tab.nb);
+  static bool configured = false;
+  if (!configured) {
+    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesX3));
+    configured = true;
+  }
+  ProfScope ps(KC_ATTN, s);
+  attention_mma_x3_kernel<true><<<grid, kThreads, kSmemBytesX3, s>>>(planes, out, nullptr, tab.t_max, H, tab);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

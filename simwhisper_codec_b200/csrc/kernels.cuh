@@ -68,6 +68,8 @@ int unpack_rows(const void* packed, void* padded, int dtype, const RaggedTable& 
 int attention_simt(const void* qkv, int type, void* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
 // bf16x3 mode: fp32-class flash attention on mma.sync over the (hi | lo) bf16 planes of the fp32 qkv rows, fp32 output
 int attention_mma_x3(const bf16* planes, float* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
+// the same over packed rows (planes and out hold tab.total rows; item b = rows [off[b], off[b] + len[b]))
+int attention_mma_x3_ragged(const bf16* planes, float* out, const RaggedTable& tab, int H, cudaStream_t s);
 // bf16 tensor-core flash attention (mma.sync m16n8k16), same contract
 int attention_mma(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
 // bf16 flash attention on tcgen05 / TMEM / TMA (attention_tc.cu), same contract

@@ -141,7 +141,7 @@ int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const
   for (size_t li = 0; li < layers.size() && !c.dry; ++li) {
     const LayerW& L = layers[li];
     // bf16x3 mode: the qkv GEMM writes the (hi | lo) planes the three-product attention kernel reads
-    const bool qkv_planes = c.m->x3() && !c.force_simt && L.qkv.w3 != nullptr && get_gemm_variant() == 2 && !rag;
+    const bool qkv_planes = c.m->x3() && !c.force_simt && L.qkv.w3 != nullptr && get_gemm_variant() == 2;
     SWC_TRY(layernorm(h, nullptr, nullptr, xn, at, L.ln1_g, L.ln1_b, 1e-5f, nb, T, T, D, nullptr, c.s));
     {
       GemmDesc d = base_desc(xn, D, 0, (int)rows, D, (int)rows, 1, L.qkv);
@@ -149,8 +149,14 @@ int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const
       d.epi.out_planes = qkv_planes;
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, qkv_planes ? 1 : at));
     }
-    if (rag) SWC_TRY(attention_tc_ragged((const bf16*)qkv, (bf16*)ao, *rag, m.heads, m.num_sms, c.s));
-    else SWC_TRY(run_attention(c, qkv, ao, lens, nb, T, qkv_planes));
+    if (rag && m.x3()) {
+      SWC_REQUIRE(qkv_planes, "bf16x3: the packed-token path needs the pair kernel's planes epilogue for qkv");
+      SWC_TRY(attention_mma_x3_ragged((const bf16*)qkv, (float*)ao, *rag, m.heads, c.s));
+    } else if (rag) {
+      SWC_TRY(attention_tc_ragged((const bf16*)qkv, (bf16*)ao, *rag, m.heads, m.num_sms, c.s));
+    } else {
+      SWC_TRY(run_attention(c, qkv, ao, lens, nb, T, qkv_planes));
+    }
     {
       GemmDesc d = base_desc(ao, D, 0, (int)rows, D, (int)rows, 1, L.out);
       set_out(d, h, D, 0);
@@ -211,10 +217,10 @@ int encoder_cl(Ctx& c, const void* mel_cl, const long long* enc_lens, int nb, in
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
     }
   }
-  const bool ragged = at == 1 && !c.force_simt && c.rag != nullptr && c.rag->nb == nb && c.rag->total > 0 && c.rag->t_max <= T;
+  const bool ragged = (at == 1 || (m.x3() && get_gemm_variant() == 2)) && !c.force_simt && c.rag != nullptr && c.rag->nb == nb && c.rag->total > 0 && c.rag->t_max <= T;
   float* hp = nullptr;
   void* xnp = nullptr;
-  if (at == 1 && (c.dry || ragged)) {       // packed residual stream and packed normalised output
+  if ((at == 1 || m.x3()) && (c.dry || ragged)) {       // packed residual stream and packed normalised output
     hp = (float*)c.ws.alloc((long long)nb * T * D * 4);
     xnp = c.ws.alloc((long long)nb * T * D * esz(at));
     SWC_TRY(c.ws.check());
@@ -327,10 +333,10 @@ int decoder_cl(Ctx& c, float* h, const long long* lens, int nb, int T, void* mel
   const Model& m = *c.m;
   const int D = m.d_model, MP = m.mel_pitch, at = m.act_type();
   const size_t mark = c.ws.mark();
-  const bool ragged = at == 1 && !c.force_simt && c.rag != nullptr && c.rag->nb == nb && c.rag->total > 0 && c.rag->t_max <= T;
+  const bool ragged = (at == 1 || (m.x3() && get_gemm_variant() == 2)) && !c.force_simt && c.rag != nullptr && c.rag->nb == nb && c.rag->total > 0 && c.rag->t_max <= T;
   float* hp = nullptr;
   void* xnp = nullptr;
-  if (at == 1 && (c.dry || ragged)) {
+  if ((at == 1 || m.x3()) && (c.dry || ragged)) {
     hp = (float*)c.ws.alloc((long long)nb * T * D * 4);
     xnp = c.ws.alloc((long long)nb * T * D * esz(at));
     SWC_TRY(c.ws.check());
@@ -550,7 +556,7 @@ int detokenize_chain(Ctx& c, const float* zq_cl, const long long* code_lens, int
   // min(Tv, 8 len_max + 80) frames; the frames beyond see the cut as a sequence end, which can reach valid samples
   // only from frame 8 len + 5 on.  Valid samples are bit-identical to the full-length computation.
   bool bucketed = false;
-  if (c.rag != nullptr && c.rag->nb == nb && !c.dry && at == 1) {
+  if (c.rag != nullptr && c.rag->nb == nb && !c.dry && (at == 1 || m.x3())) {
     bucketed = true;
     for (int b = 1; b < nb; ++b) bucketed = bucketed && c.rag->len[b] <= c.rag->len[b - 1];
   }

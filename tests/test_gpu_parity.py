@@ -226,10 +226,13 @@ def test_bf16_full_window_properties(model16, model32, gen_params, sd_ex):
     assert torch.equal(y2["y"], y16["y"])
 
 
-def test_ragged_transformer_path_is_bit_identical(model16, monkeypatch):
-    """encode()/decode() know the window lengths on the host and run the bf16 transformer stacks on the packed valid tokens
-    only; every token must come out exactly as on the padded path."""
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3"])
+def test_ragged_transformer_path_is_bit_identical(mode, model16, model_x3, monkeypatch):
+    """encode()/decode() know the window lengths on the host and run the transformer stacks on the packed valid tokens
+    only (tensor-core precisions), and Vocos only over each window's valid frames plus its halo; every token and every
+    valid sample must come out exactly as on the padded path."""
     import simwhisper_codec_b200.audiocodec.model as mm
+    model16 = model16 if mode == "bf16" else model_x3
     lens = [48123, 800000, 365000, 1280 * 250, 479999, 32000, 100, 161 * 3]
     wavs = [synthetic_wave(6000 + i, n) for i, n in enumerate(lens)]
     monkeypatch.setattr(mm, "_RAGGED", False)
