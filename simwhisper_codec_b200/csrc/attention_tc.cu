@@ -1,7 +1,7 @@
 // bf16 flash attention on tcgen05 (reference audiocodec/nn/modules.py:145-187): non-causal, head_dim 64, keys >=
 // lens[b] masked, q pre-scaled by the packed q_proj.  Persistent, warp-specialised, two 128-query tiles per work item:
 //
-//   warp 0      TMA producer: Q tiles (double-buffered per item) and a 4-stage ring of K|V tiles (128 keys x 64 x bf16 each)
+//   warp 0      TMA producer: Q tiles (double-buffered per item) and a 3-stage ring of K|V tiles (128 keys x 64 x bf16 each)
 //   warp 1, 2   MMA issuer of query tile 0 / 1 (one lane each; warp 1 also owns the TMEM allocation)
 //                 S_i = Q_i K_j^T   UMMA M128 N128 K16 x4, both operands K-major from shared memory -> TMEM (fp32)
 //                 O_i += P_i V_j    UMMA M128 N64  K16 x8, A = P_i (bf16) from TMEM, B = V_j MN-major from shared memory
@@ -9,6 +9,8 @@
 //               two warpgroups or pays ~150 cycles per polled barrier), and S runs one key block ahead of P V.
 //   warps 3-6   softmax warpgroup of query tile 0 (one thread = one query row = one TMEM lane)
 //   warps 7-10  softmax warpgroup of query tile 1
+//               (SPLIT = 2, the default: two threads share a row, 8 warps per tile, warps 3-10 / 11-18; the halves of a row
+//               exchange their maximum and their sum through shared memory behind a 64-thread named barrier of their own)
 //
 // The two tiles ping-pong: while one warpgroup exponentiates S_i(j) the tensor core computes S_{1-i} / P V of the other.
 // Per tile and key block a softmax thread reads its 128 scores from TMEM, takes the row maximum, and only when the
