@@ -81,6 +81,10 @@ int swc_mel(const swc_model* m, const float* wav, int64_t wav_stride, int wav_co
  *      mel_cf (B,80,Tm) -> enc_cf (B,768,ceil(Tm/2)), out_lens = mel_lens // 2 ---- */
 int swc_encoder(const swc_model* m, const float* mel_cf, const int64_t* mel_lens, int batch, int mel_frames,
                 float* enc_cf, int64_t* out_lens, void* workspace, size_t ws_bytes, void* stream);
+/* the same with output_hidden_states=True (modules.py:344-371): hidden_cf (n_layers + 1, B, 768, ceil(T/2)) fp32 receives the
+   input of each of the 12 layers and the final LayerNorm output, frames >= length zeroed, channels-first like enc_cf */
+int swc_encoder_hidden(const swc_model* m, const float* mel_cf, const int64_t* mel_lens, int batch, int mel_frames,
+                       float* enc_cf, int64_t* out_lens, float* hidden_cf, void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- FrameStackDownConv.forward (modules.py:519-550): (B,768,T) -> latent (B,32,ceil(T/4)) ---- */
 int swc_downsample(const swc_model* m, const float* x_cf, const int64_t* lens, int batch, int frames,
@@ -119,7 +123,9 @@ int swc_detokenize(const swc_model* m, const void* codes, int codes_are_int64, c
 /* ---- the same two chains when the caller also knows the lengths on the HOST (AudioCodec.encode()/decode() do:
  *      model.py:262-268, 327-333 build them from Python lists).  In bf16 mode the two transformer stacks then run on the
  *      packed valid tokens only (padded tokens of a window are skipped); results are bit-identical to swc_tokenize /
- *      swc_detokenize.  host_lengths[b] must equal lengths[b]; batches above 128 items fall back to the padded path. ---- */
+ *      swc_detokenize.  host_lengths[b] must equal lengths[b]; a call takes at most swc_max_ragged() items (the length table
+ *      travels as a kernel parameter): larger batches are an error, the caller splits them (AudioCodec does). ---- */
+int swc_max_ragged(void);
 int swc_tokenize_ragged(const swc_model* m, const float* wav, int64_t wav_stride, int wav_cols, const int64_t* lengths,
                         const int64_t* host_lengths, int batch, int32_t* codes, float* zq_cf, int64_t* codes_lens,
                         void* workspace, size_t ws_bytes, void* stream);

@@ -138,20 +138,27 @@ def _n_layers(sd: SD, prefix: str) -> int:
 
 
 def encoder(sd: SD, mel: torch.Tensor, mel_lens: torch.Tensor, heads: int = 12,
-            return_stem: bool = False):
+            return_stem: bool = False, output_hidden_states: bool = False):
     """OmniAudioEncoder.forward with is_acoustic=True (modules.py:287-376): two un-activated convs,
-    no positional embedding, N layers, final LN, zero the rows >= len, channels-first output."""
+    no positional embedding, N layers, final LN, zero the rows >= len, channels-first output.
+    output_hidden_states (modules.py:344-371): also the masked, transposed input of every layer and the final LN output."""
     p = "acoustic_encoder"
     x = F.conv1d(mel, sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding=1)
     x = F.conv1d(x, sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], stride=2, padding=1)
     lens = (mel_lens // 2).long()
     h = x.permute(0, 2, 1)
     stem = h
+    hidden = []
     for i in range(_n_layers(sd, p)):
+        hidden.append(h)
         h = transformer_layer(sd, f"{p}.layers.{i}", h, lens, heads)
     h = _ln(sd, p + ".layer_norm", h, 1e-5)
+    hidden.append(h)
     keep = (torch.arange(h.shape[1])[None, :] < lens[:, None])[..., None]
-    h = torch.where(keep, h, torch.zeros((), dtype=h.dtype)).transpose(1, 2)
+    mask = lambda t: torch.where(keep, t, torch.zeros((), dtype=t.dtype)).transpose(1, 2)  # noqa: E731
+    h = mask(h)
+    if output_hidden_states:
+        return h, lens, tuple(mask(t) for t in hidden)
     return (h, lens, stem) if return_stem else (h, lens)
 
 

@@ -32,6 +32,7 @@ SIGNATURES = {
     "swc_workspace_bytes": (_sz, [_p, _i, _i, _i]),
     "swc_mel": (_i, [_p, _p, _i64, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "swc_encoder": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "swc_encoder_hidden": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "swc_downsample": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
     "swc_quantize": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
     "swc_dequantize": (_i, [_p, _p, _i, _p, _i, _i, _p, _p]),
@@ -40,6 +41,7 @@ SIGNATURES = {
     "swc_vocos": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
     "swc_tokenize": (_i, [_p, _p, _i64, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "swc_detokenize": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "swc_max_ragged": (_i, []),
     "swc_tokenize_ragged": (_i, [_p, _p, _i64, _i, _p, C.POINTER(_i64), _i, _p, _p, _p, _p, _sz, _p]),
     "swc_detokenize_ragged": (_i, [_p, _p, _i, _p, C.POINTER(_i64), _i, _i, _p, _p, _p, _sz, _p]),
     "swc_forward": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),

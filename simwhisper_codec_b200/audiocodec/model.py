@@ -40,8 +40,9 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None) -> C.c_void_p:
+    """The caller's current stream ON THE TENSORS' DEVICE (not on whatever device happens to be current)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class NativeCodec:
@@ -121,7 +122,7 @@ class _Stage(_Holder):
         out_lens = torch.empty(B, dtype=torch.int64, device=x.device)
         ws, nws = nat.workspace(stage, B, frames)
         fn = getattr(nat.lib, fn_name)
-        _lib.check(fn(nat.handle, _ptr(x), _ptr(lens), B, frames, _ptr(out), _ptr(out_lens), ws, nws, _stream()), fn_name)
+        _lib.check(fn(nat.handle, _ptr(x), _ptr(lens), B, frames, _ptr(out), _ptr(out_lens), ws, nws, _stream(x.device)), fn_name)
         return out, out_lens
 
 
@@ -129,10 +130,21 @@ class OmniAudioEncoder(_Stage):
     """reference audiocodec/nn/modules.py:236-376 — forward(input_features (B,80,T), input_length)."""
 
     def forward(self, input_features, input_length, output_hidden_states=False):
-        if output_hidden_states:
-            raise NotImplementedError("output_hidden_states is not part of the codec hot path")
         B, _, T = input_features.shape
-        return self._run("swc_encoder", "encoder", input_features, input_length, (B, 768, (T + 1) // 2), T)
+        if not output_hidden_states:
+            return self._run("swc_encoder", "encoder", input_features, input_length, (B, 768, (T + 1) // 2), T)
+        # reference modules.py:344-371: additionally the input of every layer and the final LayerNorm output, masked
+        nat = self._owner._native_for(input_features.device)
+        x = input_features.contiguous().to(torch.float32)
+        lens = input_length.to(device=x.device, dtype=torch.int64).contiguous()
+        n_layers = sum(1 for k in self._owner.state_dict() if k.startswith("acoustic_encoder.layers.") and k.endswith(".fc1.bias"))
+        out = torch.empty((B, 768, (T + 1) // 2), dtype=torch.float32, device=x.device)
+        hidden = torch.empty((n_layers + 1, B, 768, (T + 1) // 2), dtype=torch.float32, device=x.device)
+        out_lens = torch.empty(B, dtype=torch.int64, device=x.device)
+        ws, nws = nat.workspace("encoder", B, T)
+        _lib.check(nat.lib.swc_encoder_hidden(nat.handle, _ptr(x), _ptr(lens), B, T, _ptr(out), _ptr(out_lens), _ptr(hidden),
+                                              ws, nws, _stream(x.device)), "swc_encoder_hidden")
+        return out, out_lens, tuple(hidden.unbind(0))
 
 
 class FrameStackDownConv(_Stage):
@@ -183,7 +195,7 @@ class GroupFiniteScalarQuantizer(_Stage):
         B, _, T = x.shape
         zq = torch.empty_like(x)
         codes = torch.empty((8, B, T), dtype=torch.int32, device=x.device)
-        _lib.check(nat.lib.swc_quantize(nat.handle, _ptr(x), _ptr(lens), B, T, _ptr(zq), _ptr(codes), _stream()), "swc_quantize")
+        _lib.check(nat.lib.swc_quantize(nat.handle, _ptr(x), _ptr(lens), B, T, _ptr(zq), _ptr(codes), _stream(x.device)), "swc_quantize")
         return zq, codes
 
     def encode(self, inputs, input_len):
@@ -200,7 +212,7 @@ class GroupFiniteScalarQuantizer(_Stage):
         _, B, T = idx.shape
         zq = torch.empty((B, 32, T), dtype=torch.float32, device=idx.device)
         _lib.check(nat.lib.swc_dequantize(nat.handle, _ptr(idx), int(idx.dtype == torch.int64), _ptr(lens), B, T,
-                                          _ptr(zq), _stream()), "swc_dequantize")
+                                          _ptr(zq), _stream(idx.device)), "swc_dequantize")
         return zq
 
 
@@ -243,10 +255,16 @@ class AudioCodec(nn.Module):
         self.num_groups = gp["quantizer"]["num_groups"]
         self.codebook_dim_per_group = len(gp["quantizer"]["num_levels_per_group"])
         self._validate(gp)
-        self.precision = precision or os.environ.get("SWC_PRECISION", "fp32")
+        # reference model.py:36-39: Whisper initialisation options ride in the encoder's config block
+        self.freeze_acoustic_encoder_flag = gp["acoustic_encoder"].get("freeze", False)
+        self.whisper_model_path = gp["acoustic_encoder"].get("whisper_model_path", None)
+        self.init_from_whisper = gp["acoustic_encoder"].get("init_from_whisper", False)
+        # default: the parity-grade tensor-core mode (meets the fp32 bars of north_star at tensor-core speed); "bf16" is the
+        # throughput mode, "fp32" the CUDA-core reference arithmetic
+        self.precision = precision or os.environ.get("SWC_PRECISION", "bf16x3")
         if self.precision not in _lib.PRECISION:
             raise ValueError(f"precision must be one of {list(_lib.PRECISION)}, got {self.precision}")
-        self.max_batch = int(max_batch or os.environ.get("SWC_MAX_BATCH", 64))
+        self.max_batch = max(1, int(max_batch or os.environ.get("SWC_MAX_BATCH", 128)))
 
         self.acoustic_encoder = OmniAudioEncoder(self, "encoder")
         self.downsample = FrameStackDownConv(self, "downsample")
@@ -293,6 +311,17 @@ class AudioCodec(nn.Module):
             raise ValueError("this build is specialised for config/SimWhisperCodec.yaml (768-d, 12 heads, 512-d "
                              "resamplers, 8x[8,7,6,6] FSQ, Vocos 512/4096, n_fft 640); other shapes have no kernels")
 
+    def _init_whisper_weights(self):
+        """reference model.py:59-88: copy the pretrained Whisper encoder into `acoustic_encoder` (utils/weight_init.py)."""
+        if not self.init_from_whisper:
+            return
+        if self.whisper_model_path is None:
+            logging.warning("init_from_whisper=True but no whisper_model_path given; skipping weight initialisation")
+            return
+        from ..utils.weight_init import load_whisper_weights
+        load_whisper_weights(encoder=self.acoustic_encoder, whisper_model_name=self.whisper_model_path,
+                             verbose=int(os.environ.get("RANK", 0)) == 0, is_acoustic=True)
+
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         r = super().load_state_dict(state_dict, strict=strict, assign=assign)
         self._version += 1
@@ -324,7 +353,7 @@ class AudioCodec(nn.Module):
         mel_lens = torch.empty(B, dtype=torch.int64, device=x2d.device)
         ws, nws = nat.workspace("mel", B, 3000)
         _lib.check(nat.lib.swc_mel(nat.handle, _ptr(x2d), x2d.stride(0), x2d.shape[1], _ptr(lens), B, _ptr(mel),
-                                   _ptr(mel_lens), ws, nws, _stream()), "swc_mel")
+                                   _ptr(mel_lens), ws, nws, _stream(x2d.device)), "swc_mel")
         return mel, mel_lens
 
     def _tokenize(self, x2d: torch.Tensor, lens: torch.Tensor, want_zq: bool, host_lens=None):
@@ -336,6 +365,8 @@ class AudioCodec(nn.Module):
         zq = torch.empty((N, 32, 375), dtype=torch.float32, device=x2d.device) if want_zq else None
         clens = torch.empty(N, dtype=torch.int64, device=x2d.device)
         mb = self.max_batch
+        if host_lens is not None and _RAGGED:
+            mb = min(mb, int(nat.lib.swc_max_ragged()))      # the packed-token path takes at most this many items per call
         for s in range(0, N, mb):
             n = min(mb, N - s)
             ws, nws = nat.workspace("tokenize", n, 3000)
@@ -345,10 +376,10 @@ class AudioCodec(nn.Module):
                 hl = (C.c_int64 * n)(*[int(v) for v in host_lens[s:s + n]])
                 _lib.check(nat.lib.swc_tokenize_ragged(nat.handle, _ptr(x2d[s:s + n]), x2d.stride(0), x2d.shape[1],
                                                        _ptr(lens[s:s + n]), hl, n, _ptr(c_part), _ptr(z_part),
-                                                       _ptr(clens[s:s + n]), ws, nws, _stream()), "swc_tokenize_ragged")
+                                                       _ptr(clens[s:s + n]), ws, nws, _stream(x2d.device)), "swc_tokenize_ragged")
             else:
                 _lib.check(nat.lib.swc_tokenize(nat.handle, _ptr(x2d[s:s + n]), x2d.stride(0), x2d.shape[1], _ptr(lens[s:s + n]),
-                                                n, _ptr(c_part), _ptr(z_part), _ptr(clens[s:s + n]), ws, nws, _stream()),
+                                                n, _ptr(c_part), _ptr(z_part), _ptr(clens[s:s + n]), ws, nws, _stream(x2d.device)),
                            "swc_tokenize")
             if N > mb:
                 codes[:, s:s + n] = c_part
@@ -361,6 +392,8 @@ class AudioCodec(nn.Module):
         wav = torch.empty((N, 1280 * Tc), dtype=torch.float32, device=codes.device)
         olens = torch.empty(N, dtype=torch.int64, device=codes.device)
         mb = self.max_batch
+        if host_lens is not None and _RAGGED:
+            mb = min(mb, int(nat.lib.swc_max_ragged()))
         for s in range(0, N, mb):
             n = min(mb, N - s)
             ws, nws = nat.workspace("detokenize", n, Tc)
@@ -369,10 +402,10 @@ class AudioCodec(nn.Module):
                 hl = (C.c_int64 * n)(*[int(v) for v in host_lens[s:s + n]])
                 _lib.check(nat.lib.swc_detokenize_ragged(nat.handle, _ptr(c_part), int(codes.dtype == torch.int64),
                                                          _ptr(lens[s:s + n]), hl, n, Tc, _ptr(wav[s:s + n]),
-                                                         _ptr(olens[s:s + n]), ws, nws, _stream()), "swc_detokenize_ragged")
+                                                         _ptr(olens[s:s + n]), ws, nws, _stream(codes.device)), "swc_detokenize_ragged")
             else:
                 _lib.check(nat.lib.swc_detokenize(nat.handle, _ptr(c_part), int(codes.dtype == torch.int64), _ptr(lens[s:s + n]), n,
-                                                  Tc, _ptr(wav[s:s + n]), _ptr(olens[s:s + n]), ws, nws, _stream()),
+                                                  Tc, _ptr(wav[s:s + n]), _ptr(olens[s:s + n]), ws, nws, _stream(codes.device)),
                            "swc_detokenize")
         return wav, olens
 
@@ -389,7 +422,7 @@ class AudioCodec(nn.Module):
         olens = torch.empty(B, dtype=torch.int64, device=mel.device)
         ws, nws = nat.workspace("forward", B, Tm)
         _lib.check(nat.lib.swc_forward(nat.handle, _ptr(mel), _ptr(lens), B, Tm, _ptr(wav), _ptr(olens), _ptr(None),
-                                       ws, nws, _stream()), "swc_forward")
+                                       ws, nws, _stream(mel.device)), "swc_forward")
         return {"reconstructed_audio": wav[:, None, :], "audio_lengths": olens}
 
     @torch.inference_mode()
@@ -464,7 +497,11 @@ class AudioCodec(nn.Module):
         src, splits = windows.encode_gather_index(lens, jobs, overlap_seconds, self.input_sample_rate,
                                                   self.max_audio_seconds, self.encoder_downsample_rate)
         flat = codes.reshape(self.num_groups, -1)
-        idx = torch.tensor(src, dtype=torch.int64).to(codes.device, non_blocking=True)
+        if (src < 0).any():                  # positions the reference leaves zero (only when the hop is not a multiple of 1280)
+            src = src.copy()
+            src[src < 0] = flat.shape[1]
+            flat = torch.cat([flat, flat.new_zeros(self.num_groups, 1)], dim=1)
+        idx = torch.from_numpy(src).to(codes.device, non_blocking=True)
         return list(torch.split(flat.index_select(1, idx), splits, dim=1))
 
     @torch.inference_mode()
@@ -474,16 +511,26 @@ class AudioCodec(nn.Module):
         device = torch.device(device)
         lens = [int(c.shape[-1]) for c in codes_list]
         up = self.decoder_upsample_rate
-        outs = [torch.empty(L * up, dtype=torch.float32, device=device) for L in lens]
+        # one flat buffer with a view per item (every sample is written by exactly one window), one fused copy for all windows
+        outs = list(torch.split(torch.empty(sum(lens) * up, dtype=torch.float32, device=device), [L * up for L in lens]))
         groups = windows.plan_decode(lens, overlap_seconds, self.input_sample_rate, self.max_audio_seconds,
                                      self.encoder_downsample_rate)
+        dst_views, src_views = [], []
         for _, jobs in groups.items():
             wav = self.decode_jobs(codes_list, jobs, device)
             for k, j in enumerate(jobs):
                 off, n = windows.decode_keep(j, overlap_seconds, self.input_sample_rate, self.max_audio_seconds,
                                              self.encoder_downsample_rate, up)
-                outs[j.item][off:off + n] = wav[k, :n]
+                dst_views.append(outs[j.item][off:off + n])
+                src_views.append(wav[k, :n])
+        if dst_views:
+            torch._foreach_copy_(dst_views, src_views)
         return {"syn_wav_list": outs}
+
+    def remove_weight_norm(self):
+        """API parity with the reference (modules.py remove_weight_norm on the resamplers): the packed weights already
+        hold g * v / ||v|| folded once at load time, so there is nothing to remove."""
+        return self
 
     @classmethod
     def load_from_checkpoint(cls, config_path: str, ckpt_path: str, **kwargs):

@@ -26,7 +26,8 @@ struct ProfState {
   std::vector<cudaEvent_t> pool;
   cudaEvent_t cur = nullptr;
 };
-static ProfState g_prof;
+// per host thread: each thread that drives a stream sees its own launch counters and timers (no shared mutable state)
+static thread_local ProfState g_prof;
 static cudaEvent_t prof_event() {
   if (!g_prof.pool.empty()) { cudaEvent_t e = g_prof.pool.back(); g_prof.pool.pop_back(); return e; }
   cudaEvent_t e;
@@ -65,6 +66,16 @@ int make_ctx(const swc_model* mm, void* ws, size_t ws_bytes, void* stream, Ctx& 
   const char* f = getenv("SWC_FORCE_SIMT");
   c.force_simt = f && f[0] == '1';
   SWC_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  return 0;
+}
+
+// a device pointer handed to an entry point must live on the model's device (the kernels and tensor maps are issued there)
+int check_on_device(int device, const void* p, const char* what) {
+  if (!p) return 0;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  SWC_REQUIRE(a.type != cudaMemoryTypeDevice || a.device == device, "%s lives on device %d but the model was finalized on device %d",
+              what, a.device, device);
   return 0;
 }
 
@@ -258,24 +269,39 @@ size_t swc_workspace_bytes(const swc_model* mm, int stage, int B, int frames) {
 #define SWC_ENTER()                                  \
   Ctx c;                                             \
   SWC_TRY(make_ctx(m, workspace, ws_bytes, stream, c)); \
-  SWC_REQUIRE(batch > 0, "empty batch")
+  SWC_REQUIRE(batch > 0, "empty batch");             \
+  DeviceGuard guard(m->m.device);                    \
+  SWC_REQUIRE(guard.ok(), "cannot make device %d current", m->m.device); \
+  SWC_TRY(check_on_device(m->m.device, workspace, "workspace"))
 
 int swc_mel(const swc_model* m, const float* wav, int64_t wav_stride, int wav_cols, const int64_t* lengths, int batch,
             float* mel_cf, int64_t* mel_lens, void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();
+  SWC_TRY(check_on_device(m->m.device, wav, "wav"));
   return stage_mel(c, wav, wav_stride, wav_cols, (const long long*)lengths, batch, mel_cf, (long long*)mel_lens);
 }
 
 int swc_encoder(const swc_model* m, const float* mel_cf, const int64_t* mel_lens, int batch, int mel_frames, float* enc_cf,
                 int64_t* out_lens, void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();
+  SWC_TRY(check_on_device(m->m.device, mel_cf, "mel_cf"));
   SWC_REQUIRE(mel_frames > 0, "encoder: no frames");
+  return stage_encoder(c, mel_cf, (const long long*)mel_lens, batch, mel_frames, enc_cf, (long long*)out_lens);
+}
+
+int swc_encoder_hidden(const swc_model* m, const float* mel_cf, const int64_t* mel_lens, int batch, int mel_frames, float* enc_cf,
+                       int64_t* out_lens, float* hidden_cf, void* workspace, size_t ws_bytes, void* stream) {
+  SWC_ENTER();
+  SWC_TRY(check_on_device(m->m.device, mel_cf, "mel_cf"));
+  SWC_REQUIRE(mel_frames > 0 && hidden_cf != nullptr, "encoder_hidden: no frames or no output buffer");
+  c.hidden_out = hidden_cf;
   return stage_encoder(c, mel_cf, (const long long*)mel_lens, batch, mel_frames, enc_cf, (long long*)out_lens);
 }
 
 int swc_downsample(const swc_model* m, const float* x_cf, const int64_t* lens, int batch, int frames, float* latent_cf,
                    int64_t* out_lens, void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();
+  SWC_TRY(check_on_device(m->m.device, x_cf, "x_cf"));
   SWC_REQUIRE(frames > 0, "downsample: no frames");
   return stage_downsample(c, x_cf, (const long long*)lens, batch, frames, latent_cf, (long long*)out_lens);
 }
@@ -283,42 +309,53 @@ int swc_downsample(const swc_model* m, const float* x_cf, const int64_t* lens, i
 int swc_quantize(const swc_model* m, const float* latent_cf, const int64_t* lens, int batch, int frames, float* zq_cf,
                  int32_t* codes, void* stream) {
   SWC_REQUIRE(m && m->m.uploaded, "model is not finalized on a CUDA device");
+  DeviceGuard guard(m->m.device);
+  SWC_REQUIRE(guard.ok(), "cannot make device %d current", m->m.device);
+  SWC_TRY(check_on_device(m->m.device, latent_cf, "latent"));
   return fsq_encode_cf(latent_cf, (const long long*)lens, batch, frames, m->m.fsq, zq_cf, codes, nullptr, (cudaStream_t)stream);
 }
 
 int swc_dequantize(const swc_model* m, const void* codes, int codes_are_int64, const int64_t* lens, int batch, int frames,
                    float* zq_cf, void* stream) {
   SWC_REQUIRE(m && m->m.uploaded, "model is not finalized on a CUDA device");
+  DeviceGuard guard(m->m.device);
+  SWC_REQUIRE(guard.ok(), "cannot make device %d current", m->m.device);
+  SWC_TRY(check_on_device(m->m.device, codes, "codes"));
   return fsq_decode(codes, codes_are_int64, (const long long*)lens, batch, frames, m->m.fsq, zq_cf, nullptr, (cudaStream_t)stream);
 }
 
 int swc_upsample(const swc_model* m, const float* zq_cf, const int64_t* lens, int batch, int frames, float* y_cf,
                  int64_t* out_lens, void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();
+  SWC_TRY(check_on_device(m->m.device, zq_cf, "zq_cf"));
   return stage_upsample(c, zq_cf, (const long long*)lens, batch, frames, y_cf, (long long*)out_lens);
 }
 
 int swc_decoder(const swc_model* m, const float* x_cf, const int64_t* lens, int batch, int frames, float* mel_cf,
                 int64_t* out_lens, void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();
+  SWC_TRY(check_on_device(m->m.device, x_cf, "x_cf"));
   return stage_decoder(c, x_cf, (const long long*)lens, batch, frames, mel_cf, (long long*)out_lens);
 }
 
 int swc_vocos(const swc_model* m, const float* mel_cf, const int64_t* lens, int batch, int frames, float* wav,
               int64_t* out_lens, void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();
+  SWC_TRY(check_on_device(m->m.device, mel_cf, "mel_cf"));
   return stage_vocos(c, mel_cf, (const long long*)lens, batch, frames, wav, (long long*)out_lens);
 }
 
 int swc_tokenize(const swc_model* m, const float* wav, int64_t wav_stride, int wav_cols, const int64_t* lengths, int batch,
                  int32_t* codes, float* zq_cf, int64_t* codes_lens, void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();
+  SWC_TRY(check_on_device(m->m.device, wav, "wav"));
   return tokenize_chain(c, wav, wav_stride, wav_cols, (const long long*)lengths, batch, codes, zq_cf, (long long*)codes_lens);
 }
 
 int swc_detokenize(const swc_model* m, const void* codes, int codes_are_int64, const int64_t* lens, int batch, int code_frames,
                    float* wav, int64_t* out_lens, void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();
+  SWC_TRY(check_on_device(m->m.device, codes, "codes"));
   SWC_REQUIRE(code_frames > 0, "detokenize: no code frames");
   return stage_detokenize(c, codes, codes_are_int64, (const long long*)lens, batch, code_frames, wav, (long long*)out_lens);
 }
@@ -327,7 +364,7 @@ int swc_detokenize(const swc_model* m, const void* codes, int codes_are_int64, c
 // the padded path, which gives identical results).
 static bool build_ragged(RaggedTable& tab, const int64_t* host_lens, int batch, int mode /*0 samples -> tokens, 1 code frames -> tokens*/,
                          int limit) {
-  if (!host_lens || batch <= 0 || batch > kMaxRagged) return false;
+  if (!host_lens || batch <= 0) return false;
   tab.nb = batch; tab.total = 0; tab.t_max = 0;
   for (int b = 0; b < batch; ++b) {
     long long l = host_lens[b] < 0 ? 0 : host_lens[b];
@@ -348,10 +385,14 @@ static bool build_ragged(RaggedTable& tab, const int64_t* host_lens, int batch, 
   return tab.total > 0;
 }
 
+int swc_max_ragged(void) { return kMaxRagged; }
+
 int swc_tokenize_ragged(const swc_model* m, const float* wav, int64_t wav_stride, int wav_cols, const int64_t* lengths,
                         const int64_t* host_lengths, int batch, int32_t* codes, float* zq_cf, int64_t* codes_lens,
                         void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();
+  SWC_TRY(check_on_device(m->m.device, wav, "wav"));
+  SWC_REQUIRE(batch <= kMaxRagged, "swc_tokenize_ragged: %d items exceed swc_max_ragged() = %d; split the batch", batch, kMaxRagged);
   RaggedTable tab;
   if ((m->m.act_type() == 1 || m->m.x3()) && build_ragged(tab, host_lengths, batch, 0, wav_cols < 480000 ? wav_cols : 480000)) c.rag = &tab;
   return tokenize_chain(c, wav, wav_stride, wav_cols, (const long long*)lengths, batch, codes, zq_cf, (long long*)codes_lens);
@@ -361,7 +402,9 @@ int swc_detokenize_ragged(const swc_model* m, const void* codes, int codes_are_i
                           const int64_t* host_lens, int batch, int code_frames, float* wav, int64_t* out_lens, void* workspace,
                           size_t ws_bytes, void* stream) {
   SWC_ENTER();
+  SWC_TRY(check_on_device(m->m.device, codes, "codes"));
   SWC_REQUIRE(code_frames > 0, "detokenize: no code frames");
+  SWC_REQUIRE(batch <= kMaxRagged, "swc_detokenize_ragged: %d items exceed swc_max_ragged() = %d; split the batch", batch, kMaxRagged);
   RaggedTable tab;
   if ((m->m.act_type() == 1 || m->m.x3()) && build_ragged(tab, host_lens, batch, 1, code_frames)) c.rag = &tab;
   return stage_detokenize(c, codes, codes_are_int64, (const long long*)lens, batch, code_frames, wav, (long long*)out_lens);
@@ -370,6 +413,7 @@ int swc_detokenize_ragged(const swc_model* m, const void* codes, int codes_are_i
 int swc_forward(const swc_model* m, const float* mel_cf, const int64_t* mel_lens, int batch, int mel_frames, float* wav,
                 int64_t* out_lens, int32_t* codes, void* workspace, size_t ws_bytes, void* stream) {
   SWC_ENTER();
+  SWC_TRY(check_on_device(m->m.device, mel_cf, "mel_cf"));
   return stage_forward(c, mel_cf, (const long long*)mel_lens, batch, mel_frames, wav, (long long*)out_lens, codes);
 }
 

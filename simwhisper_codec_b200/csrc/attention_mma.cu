@@ -406,11 +406,7 @@ constexpr int kSmemBytes = QT * 128 + 4 * KT * 128;
 
 int attention_mma(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, cudaStream_t s) {
   dim3 grid(ceil_div(T, QT), H, nb);
-  static bool configured = false;
-  if (!configured) {
-    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
-  }
+  SWC_TRY(ensure_dynamic_smem((const void*)attention_mma_kernel, kSmemBytes));
   ProfScope ps(KC_ATTN, s);
   attention_mma_kernel<<<grid, kThreads, kSmemBytes, s>>>(qkv, out, lens, T, H);
   SWC_CHECK_CUDA(cudaGetLastError());
@@ -419,11 +415,7 @@ int attention_mma(const bf16* qkv, bf16* out, const long long* lens, int nb, int
 
 int attention_mma_x3(const bf16* planes, float* out, const long long* lens, int nb, int T, int H, cudaStream_t s) {
   dim3 grid(ceil_div(T, QT), H, nb);
-  static bool configured = false;
-  if (!configured) {
-    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesX3));
-    configured = true;
-  }
+  SWC_TRY(ensure_dynamic_smem((const void*)attention_mma_x3_kernel<false>, kSmemBytesX3));
   ProfScope ps(KC_ATTN, s);
   attention_mma_x3_kernel<false><<<grid, kThreads, kSmemBytesX3, s>>>(planes, out, lens, T, H, RaggedTable{});
   SWC_CHECK_CUDA(cudaGetLastError());
@@ -433,11 +425,7 @@ int attention_mma_x3(const bf16* planes, float* out, const long long* lens, int 
 int attention_mma_x3_ragged(const bf16* planes, float* out, const RaggedTable& tab, int H, cudaStream_t s) {
   SWC_REQUIRE(tab.nb > 0 && tab.nb <= kMaxRagged && tab.total > 0 && tab.t_max > 0, "attention_mma_x3_ragged: bad table");
   dim3 grid(ceil_div(tab.t_max, QT), H, tab.nb);
-  static bool configured = false;
-  if (!configured) {
-    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesX3));
-    configured = true;
-  }
+  SWC_TRY(ensure_dynamic_smem((const void*)attention_mma_x3_kernel<true>, kSmemBytesX3));
   ProfScope ps(KC_ATTN, s);
   attention_mma_x3_kernel<true><<<grid, kThreads, kSmemBytesX3, s>>>(planes, out, nullptr, tab.t_max, H, tab);
   SWC_CHECK_CUDA(cudaGetLastError());

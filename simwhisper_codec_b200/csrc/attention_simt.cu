@@ -162,12 +162,8 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const T* __restrict
 
 int attention_simt(const void* qkv, int type, void* out, const long long* lens, int nb, int T, int H, cudaStream_t s) {
   dim3 grid(ceil_div(T, QT), H, nb);
-  static bool configured = false;
-  if (!configured) {
-    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    SWC_CHECK_CUDA(cudaFuncSetAttribute(attention_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
-  }
+  SWC_TRY(ensure_dynamic_smem((const void*)attention_simt_kernel<float>, kSmemBytes));
+  SWC_TRY(ensure_dynamic_smem((const void*)attention_simt_kernel<bf16>, kSmemBytes));
   ProfScope ps(KC_ATTN, s);
   if (type == 0) attention_simt_kernel<float><<<grid, 256, kSmemBytes, s>>>((const float*)qkv, (float*)out, lens, T, H);
   else attention_simt_kernel<bf16><<<grid, 256, kSmemBytes, s>>>((const bf16*)qkv, (bf16*)out, lens, T, H);

@@ -57,6 +57,8 @@ struct AttnParams {
   int T, H, nb, n_qp, n_items;
   FastDiv by_qp, by_h, by_qph;
   long long* trace;        // optional per-phase clock64 stamps of CTA 0 (tools/attn_trace.py); null in normal runs
+  int fine;                // trace: four more stamps per key block (perturbs the kernel)
+  int skew;                // cycles the softmax warps of query tile 1 wait at kernel start (phase offset between the tiles)
 };
 // RAGGED: rows are packed (item b = rows [off[b], off[b] + len[b])), lengths come with the launch (no global load per
 // item), and rows >= len[b] do not exist: nothing is written for them.
@@ -106,7 +108,7 @@ __device__ __forceinline__ Item decode_item(const AttnParams& p, const TAB& tab,
 }
 
 __device__ __forceinline__ void trace_stamp(const AttnParams& p, int slot, int& idx) {
-  // slots: 0 softmax warp of tile 0, 1 issuer of tile 0, 2 TMA producer; 4096 stamps each
+  // slots: 0 / 1 first softmax warp of query tile 0 / 1; 4096 stamps each
   if (p.trace && blockIdx.x == 0 && idx < 4096) p.trace[slot * 4096 + idx++] = clock64();
 }
 __device__ __forceinline__ float ex2(float x) {
@@ -119,6 +121,12 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -309,12 +317,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
     const int row = lg * 32 + lane;                   // query row inside the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
     const int DO = p.H * HD;
-    float* xch = reinterpret_cast<float*>(smem + kXchOff) + i * (2 * SPLIT * QT);   // [2 buffers][SPLIT][128 rows]
+    const uint32_t xch = smem_u32(smem + kXchOff) + (uint32_t)(i * (2 * SPLIT * QT) + row) * 4u;   // [2 buffers][SPLIT][128 rows]
     uint32_t s_cnt = 0, o_cnt = 0, x_cnt = 0;
     int tr = 0;
-    const bool tracer = (warp == 3 && lane == 0);
+    const bool tracer = p.trace != nullptr && lg == 3 && part == 0 && lane == 0;   // first softmax warp of each tile
+    const int tslot = i;
     uint8_t* ostage = smem + kOutOff + i * kTileBytes;
     long long len_next = blockIdx.x < p.n_items ? item_len_raw(p, tab, blockIdx.x) : 0;
+    if (p.skew > 0 && i == 1) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.skew) {}
+    }
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const Item it = decode_item(p, tab, item, len_next);
       if (item + (int)gridDim.x < p.n_items) len_next = item_len_raw(p, tab, item + gridDim.x);   // in flight during this item
@@ -328,10 +341,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         continue;
       }
       float m_used = -INFINITY, l = 0.f;
-      if (tracer) trace_stamp(p, 0, tr);                 // A: item decoded
+      if (tracer) trace_stamp(p, tslot, tr);                 // A: item decoded
       for (int j = 0; j < it.n_kt; ++j) {
         mbar_wait(&s_full[i], s_cnt & 1);
-        if (tracer) trace_stamp(p, 0, tr);               // B: S ready
+        if (tracer) trace_stamp(p, tslot, tr);               // B: S ready
         ++s_cnt;
         tc_fence_after();
         uint32_t s[NC];
@@ -341,9 +354,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           for (int c = 0; c < NC / 32; ++c) tmem_ld32(sa + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
           tmem_ld_wait();
         }
-#ifdef SWC_ATTN_FINE_TRACE
-        if (tracer) trace_stamp(p, 0, tr);               // B1: S in registers
-#endif
+        if (tracer && p.fine) trace_stamp(p, tslot, tr);               // B1: S in registers
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[i]);
@@ -360,16 +371,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         }
         float mxl = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kLog2e;
         if constexpr (SPLIT > 1) {                    // combine the parts' maxima (double-buffered exchange slots)
-          float* slot = xch + (x_cnt & 1) * (SPLIT * QT);
+          const uint32_t slot = xch + (x_cnt & 1) * (SPLIT * QT * 4);
           ++x_cnt;
-          slot[part * QT + row] = mxl;
+          sts_f32(slot + part * QT * 4, mxl);
           named_bar_sync(pair_bar, 32 * SPLIT);
-#pragma unroll
-          for (int o = 0; o < SPLIT; ++o) mxl = fmaxf(mxl, slot[o * QT + row]);
+          mxl = fmaxf(mxl, lds_f32(slot + (part ^ 1) * QT * 4));
         }
-#ifdef SWC_ATTN_FINE_TRACE
-        if (tracer) trace_stamp(p, 0, tr);               // B2: row maximum known
-#endif
+        if (tracer && p.fine) trace_stamp(p, tslot, tr);               // B2: row maximum known
         float scale = 1.0f;
         const bool grow = mxl > m_used + kRescaleThreshold;     // always true for j == 0 (m_used = -inf)
         if (grow) { scale = ex2(m_used - mxl); m_used = mxl; }   // j == 0: scale = 0, l = 0, O not yet written
@@ -387,9 +395,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         }
         const float bsum = (sum[0] + sum[1]) + (sum[2] + sum[3]);
         l = fmaf(l, scale, bsum);                       // this part's share of the row sum
-#ifdef SWC_ATTN_FINE_TRACE
-        if (tracer) trace_stamp(p, 0, tr);               // B3: exponentials done
-#endif
+        if (tracer && p.fine) trace_stamp(p, tslot, tr);               // B3: exponentials done
         if (j > 0) {
           mbar_wait(&o_done[i], o_cnt & 1);             // P_i(j-1) V accumulated: P_i is free, O_i is stable
           ++o_cnt;
@@ -404,9 +410,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
             tmem_st_n<ND>(oa, o);
           }
         }
-#ifdef SWC_ATTN_FINE_TRACE
-        if (tracer) trace_stamp(p, 0, tr);               // B4: previous P V done (P slot free)
-#endif
+        if (tracer && p.fine) trace_stamp(p, tslot, tr);               // B4: previous P V done (P slot free)
         {
           const uint32_t pa = lane_addr + kColP + i * 64 + part * (NC / 2);
 #pragma unroll
@@ -416,11 +420,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[i]);
-        if (tracer) trace_stamp(p, 0, tr);               // C: P handed over
+        if (tracer) trace_stamp(p, tslot, tr);               // C: P handed over
       }
       // ---- final: O_i / l -> bf16 rows
       mbar_wait(&o_done[i], o_cnt & 1);
-      if (tracer) trace_stamp(p, 0, tr);                 // D: last P V done
+      if (tracer) trace_stamp(p, tslot, tr);                 // D: last P V done
       ++o_cnt;
       tc_fence_after();
       uint32_t o[ND];
@@ -430,13 +434,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[i]);
       if constexpr (SPLIT > 1) {                        // total row sum over the parts
-        float* slot = xch + (x_cnt & 1) * (SPLIT * QT);
+        const uint32_t slot = xch + (x_cnt & 1) * (SPLIT * QT * 4);
         ++x_cnt;
-        slot[part * QT + row] = l;
+        sts_f32(slot + part * QT * 4, l);
         named_bar_sync(pair_bar, 32 * SPLIT);
-        l = 0.f;
-#pragma unroll
-        for (int o2 = 0; o2 < SPLIT; ++o2) l += slot[o2 * QT + row];
+        l += lds_f32(slot + (part ^ 1) * QT * 4);
       }
       const float inv = (q < it.len && l > 0.f) ? 1.0f / l : 0.f;     // padded query rows -> 0
       {
@@ -467,7 +469,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           if (r < row_limit) *reinterpret_cast<uint4*>(obase + (long long)r * DO + c * 8) = v;
         }
       }
-      if (tracer) trace_stamp(p, 0, tr);                 // E: item stored
+      if (tracer) trace_stamp(p, tslot, tr);                 // E: item stored
     }
   }
 
@@ -482,7 +484,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
 
 }  // namespace
 
-long long* g_attn_trace = nullptr;   // set by swc_debug_attn_trace_enable
+long long* g_attn_trace = nullptr;   // set by swc_debug_attn_trace
+int g_attn_trace_fine = 0;
 
 namespace {
 template <typename TAB>
@@ -503,15 +506,14 @@ int attention_tc_launch(const bf16* qkv, bf16* out, const long long* lens, long 
   SWC_REQUIRE((long long)p.n_items * std::max(p.n_qp * H, 1) < (1ll << 32), "attention_tc: too many work items (%d)", p.n_items);
   p.by_qp.set((uint32_t)p.n_qp); p.by_h.set((uint32_t)H); p.by_qph.set((uint32_t)(p.n_qp * H));
   p.trace = g_attn_trace;
+  p.fine = g_attn_trace_fine;
+  static const int skew = [] { const char* e = getenv("SWC_ATTN_SKEW"); return e ? atoi(e) : 0; }();
+  p.skew = skew;
   static const int split = [] { const char* e = getenv("SWC_ATTN_SPLIT"); return (e && e[0] == '1') ? 1 : 2; }();
   const int grid = std::min(p.n_items, num_sms);
   ProfScope ps(KC_ATTN, s);
   auto go = [&](auto kern, int threads) -> int {
-    static bool configured = false;                  // one flag per instantiation (the lambda body is instantiated per kernel)
-    if (!configured) {
-      SWC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      configured = true;
-    }
+    SWC_TRY(ensure_dynamic_smem((const void*)kern, kSmemBytes));
     kern<<<grid, threads, kSmemBytes, s>>>(tm, p, tab);
     return 0;
   };
@@ -539,6 +541,7 @@ extern "C" int swc_debug_attn_trace(int enable, long long* host_out, int n) {
   if (enable) {
     if (!g_attn_trace && cudaMalloc(&g_attn_trace, 3 * 4096 * sizeof(long long)) != cudaSuccess) return -1;
     cudaMemset(g_attn_trace, 0, 3 * 4096 * sizeof(long long));
+    g_attn_trace_fine = (enable & 2) ? 1 : 0;
     return 0;
   }
   if (!g_attn_trace) return -1;

@@ -31,6 +31,24 @@ void set_error(const char* fmt, ...);
     if (_r != 0) return _r;                                                                    \
   } while (0)
 
+// opt a kernel into `bytes` of dynamic shared memory on the current device (once per device and function; gemm_tc2.cu)
+int ensure_dynamic_smem(const void* func, int bytes);
+
+// makes `device` current for the lifetime of the object and restores the caller's device afterwards: every C entry point
+// launches on the model's device whatever the process's current device is (torch.cuda.set_device elsewhere, threads, ...)
+struct DeviceGuard {
+  int prev = -1, want = -1;
+  bool good = true;
+  explicit DeviceGuard(int device) : want(device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { good = false; return; }
+    if (prev != device && cudaSetDevice(device) != cudaSuccess) good = false;
+  }
+  ~DeviceGuard() { if (good && prev >= 0 && prev != want) cudaSetDevice(prev); }
+  bool ok() const { return good; }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // ---- per-kernel-class launch counters and (optional) CUDA-event timers ------------------------------
 enum KClass { KC_GEMM_TC = 0, KC_GEMM_SIMT, KC_ATTN, KC_LAYERNORM, KC_DWCONV_LN, KC_SNAKE, KC_MISC, KC_COUNT };
 void prof_begin(int cls, cudaStream_t s);

@@ -18,12 +18,29 @@
 // time share A rows in L2.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
+#include <set>
 #include <type_traits>
+#include <utility>
 
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
 
 namespace swc {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device, per-function setting: remember the (device, function)
+// pairs that have it instead of one process-wide flag, so a second GPU in the same process gets its opt-in too.
+int ensure_dynamic_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  SWC_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({dev, func})) return 0;
+  SWC_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert({dev, func});
+  return 0;
+}
 
 EncodeTiledFn tmap_encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -415,11 +432,7 @@ int launch2(const GemmDesc& d, int num_sms, cudaStream_t s) {
   for (int i = 0; i < d.n_taps; ++i) { p.tap_row[i] = d.tap_row[i]; p.tap_col[i] = d.tap_col[i]; }
   p.bias = d.epi.bias; p.gamma = d.epi.gamma;
   auto kern = gemm_tc2_kernel<CG, STAGES, NBUF, EW, ACT, GAMMA, REDUCE, TO, PLANES>;
-  static bool configured = false;
-  if (!configured) {
-    SWC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
-  }
+  SWC_TRY(ensure_dynamic_smem((const void*)kern, L::kTotal));
   const long long total = (long long)p.m_tiles * p.n_tiles * p.nb;
   const int grid = CG * (int)std::min<long long>(total, num_sms / CG);
   cudaLaunchConfig_t cfg{};

@@ -517,14 +517,15 @@ int cf_to_cl(const float* in, void* out, int out_type, int nb, int C, int T, int
 
 template <typename TI>
 __global__ void cl_to_cf_kernel(const TI* __restrict__ in, float* __restrict__ out, int C, int T,
-                                long long in_batch_stride, int c_pitch) {
+                                long long in_batch_stride, int c_pitch, const long long* __restrict__ lens) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
+  const int t_valid = lens ? (int)(lens[b] < 0 ? 0 : (lens[b] > T ? T : lens[b])) : T;    // rows >= lens[b] read as zero
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;
   for (int i = ty; i < 32; i += 8) {
     const int t = t0 + i, c = c0 + tx;
-    tile[i][tx] = (t < T && c < C) ? to_f32<TI>(in[(long long)b * in_batch_stride + (long long)t * c_pitch + c]) : 0.f;
+    tile[i][tx] = (t < t_valid && c < C) ? to_f32<TI>(in[(long long)b * in_batch_stride + (long long)t * c_pitch + c]) : 0.f;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
@@ -533,11 +534,12 @@ __global__ void cl_to_cf_kernel(const TI* __restrict__ in, float* __restrict__ o
   }
 }
 
-int cl_to_cf(const void* in, int in_type, float* out, int nb, int C, int T, long long in_batch_stride, int c_pitch, cudaStream_t s) {
+int cl_to_cf(const void* in, int in_type, float* out, int nb, int C, int T, long long in_batch_stride, int c_pitch, cudaStream_t s,
+             const long long* lens) {
   dim3 grid(ceil_div(T, 32), ceil_div(C, 32), nb), block(32, 8);
   ProfScope ps(KC_MISC, s);
-  if (in_type == 0) cl_to_cf_kernel<float><<<grid, block, 0, s>>>((const float*)in, out, C, T, in_batch_stride, c_pitch);
-  else cl_to_cf_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)in, out, C, T, in_batch_stride, c_pitch);
+  if (in_type == 0) cl_to_cf_kernel<float><<<grid, block, 0, s>>>((const float*)in, out, C, T, in_batch_stride, c_pitch, lens);
+  else cl_to_cf_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)in, out, C, T, in_batch_stride, c_pitch, lens);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -30,7 +30,9 @@ int fsq_decode(const void* codes, int codes_i64, const long long* lens, int nb, 
 
 // layout conversion: channels-first fp32 (nb,C,T) <-> channel-last (nb,T_rows,Cpitch)
 int cf_to_cl(const float* in, void* out, int out_type, int nb, int C, int T, int t_rows, int c_pitch, cudaStream_t s);
-int cl_to_cf(const void* in, int in_type, float* out, int nb, int C, int T, long long in_batch_stride, int c_pitch, cudaStream_t s);
+// lens (optional): rows t >= lens[b] are written as zero
+int cl_to_cf(const void* in, int in_type, float* out, int nb, int C, int T, long long in_batch_stride, int c_pitch, cudaStream_t s,
+             const long long* lens = nullptr);
 
 // log-mel helpers
 int mel_pad(const float* wav, long long wav_stride, int wav_cols, const long long* lens, int nb,
@@ -46,13 +48,13 @@ int mel_finalize(const float* logmel /*(nb,3000,80)*/, const float* item_max, in
 int istft_ola(const float* frames, const float* win_sq /*[640]*/, int nb, int T, float* wav, long long wav_stride, cudaStream_t s);
 
 // ---- ragged (packed valid tokens) transformer path: per-item token counts known on the host --------------------
-constexpr int kMaxRagged = 128;
+constexpr int kMaxRagged = 256;      // items per ragged call: the table travels as a 2 KB kernel parameter (callers split larger batches)
 // bf16x3 mode: fp32 rows (nb, rows, cols; row / batch strides in elements) -> bf16 planes (nb, rows, 2 cols) = (hi | lo),
 // hi = bf16(x), lo = bf16(x - hi).  cols % 8 == 0.
 int split_bf16_planes(const float* in, long long row_stride, long long batch_stride, int nb, int rows, int cols, bf16* planes,
                       cudaStream_t s);
 
-struct RaggedTable {          // passed by value to kernels (1 KB)
+struct RaggedTable {          // passed by value to kernels (2 KB)
   int nb = 0;
   int t_max = 0;              // longest item
   int total = 0;              // sum of len

@@ -383,7 +383,8 @@ static void* g_slab_unused = nullptr;
 
 int upload_model(Model& m, int device) {
   SWC_REQUIRE(m.packed, "upload before pack");
-  SWC_CHECK_CUDA(cudaSetDevice(device));
+  DeviceGuard guard(device);            // the caller's current device is restored on every return path
+  SWC_REQUIRE(guard.ok(), "cudaSetDevice(%d) failed", device);
   cudaDeviceProp prop;
   SWC_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
   SWC_REQUIRE(prop.major == 10, "libswc is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);

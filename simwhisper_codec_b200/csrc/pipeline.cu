@@ -142,6 +142,8 @@ int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const
     const LayerW& L = layers[li];
     // bf16x3 mode: the qkv GEMM writes the (hi | lo) planes the three-product attention kernel reads
     const bool qkv_planes = c.m->x3() && !c.force_simt && L.qkv.w3 != nullptr && get_gemm_variant() == 2;
+    if (c.hidden_out && !rag)      // the layer's input, masked and channels-first
+      SWC_TRY(cl_to_cf(h, 0, c.hidden_out + (long long)li * nb * D * T, nb, D, T, (long long)T * D, D, c.s, lens));
     SWC_TRY(layernorm(h, nullptr, nullptr, xn, at, L.ln1_g, L.ln1_b, 1e-5f, nb, T, T, D, nullptr, c.s));
     {
       GemmDesc d = base_desc(xn, D, 0, (int)rows, D, (int)rows, 1, L.qkv);
@@ -233,6 +235,8 @@ int encoder_cl(Ctx& c, const void* mel_cl, const long long* enc_lens, int nb, in
   } else {
     SWC_TRY(transformer_stack(c, m.enc_layers, h, enc_lens, nb, T));
     if (!c.dry) SWC_TRY(layernorm(h, nullptr, nullptr, enc_cl, at, m.enc_ln_g, m.enc_ln_b, 1e-5f, nb, T, T4, D, enc_lens, c.s));
+    if (!c.dry && c.hidden_out)
+      SWC_TRY(cl_to_cf(enc_cl, at, c.hidden_out + (long long)m.enc_layers.size() * nb * D * T, nb, D, T, (long long)T4 * D, D, c.s));
   }
   c.ws.release(mark);
   return 0;
@@ -561,7 +565,9 @@ int detokenize_chain(Ctx& c, const float* zq_cl, const long long* code_lens, int
     for (int b = 1; b < nb; ++b) bucketed = bucketed && c.rag->len[b] <= c.rag->len[b - 1];
   }
   if (bucketed) {
-    constexpr int kHalo = 80;
+    // receptive field of a valid sample: 3 frames per depthwise convolution and for the embedding, + 1 for the overlap-add,
+    // rounded up to 8 (24 ConvNeXt blocks: 77 -> 80); derived from the model so another depth cannot silently corrupt frames
+    const int kHalo = (3 * ((int)m.voc_blocks.size() + 1) + 2 + 7) / 8 * 8;
     constexpr long long kMinRows = 40000;            // >= two waves of 256-row tile pairs per GEMM launch
     auto need = [&](int b) { return std::min(Tv, 2 * c.rag->len[b] + kHalo); };      // len = tokens = 4 x code frames
     const size_t mel_row = (size_t)m.mel_pitch * esz(at);

@@ -34,6 +34,8 @@ struct Ctx {
   Arena ws;
   bool dry = false;          // size the workspace only, launch nothing
   bool force_simt = false;   // debugging: run bf16 operands through the SIMT kernels
+  float* hidden_out = nullptr;        // encoder only: (n_layers + 1, nb, 768, T) fp32 channels-first, the input of every layer and the
+                                      // final LayerNorm output, rows >= len zeroed (reference modules.py:344-371 output_hidden_states)
   const RaggedTable* rag = nullptr;   // bf16 mode: run the transformer stacks on packed valid tokens (host-known lengths)
 };
 

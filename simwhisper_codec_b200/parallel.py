@@ -4,6 +4,12 @@ One process per GPU (torch.distributed, NCCL on GPUs / gloo in the CPU tests).  
 utterance list, plans the same global window list (windows.py), computes only its shard, and the outputs are
 gathered — there is no collective inside the forward.  The decode pad length T' is part of the global plan, so
 shards reproduce the single-GPU (= reference) result exactly.
+
+What travels:
+  * encode: the codes of every window, 12 KB each — all-gathered, so every rank holds `codes_list` (decode() needs it
+    on every rank, and it is four orders of magnitude less data than the audio);
+  * decode: waveforms (1.9 MB per window) go to ONE rank (`dst`, the caller's) with `dist.gather`, or nowhere
+    (`gather_wav=False`: every rank keeps the windows it decoded, e.g. to write them to disk itself).
 """
 from __future__ import annotations
 
@@ -15,30 +21,51 @@ import torch.distributed as dist
 from . import windows
 
 
-def _gather_rows(local: torch.Tensor, counts: List[int], group) -> torch.Tensor:
-    """all_gather of tensors (n_r, ...) with different n_r -> concatenation in rank order."""
+def _pad_rows(local: torch.Tensor, nmax: int) -> torch.Tensor:
+    if local.shape[0] == nmax:
+        return local.contiguous()
+    pad = torch.empty((nmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    return pad
+
+
+def _all_gather_rows(local: torch.Tensor, counts: List[int], group) -> List[torch.Tensor]:
+    """tensors (n_r, ...) with different n_r -> per-rank list [(n_r, ...)] on every rank."""
     world = dist.get_world_size(group)
     if world == 1:
-        return local
+        return [local]
     nmax = max(counts) if counts else 0
-    pad = torch.zeros((nmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    return torch.cat([b[:n] for b, n in zip(bufs, counts)], dim=0)
+    out = torch.empty((world * nmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)   # concatenated along dim 0
+    dist.all_gather_into_tensor(out, _pad_rows(local, nmax), group=group)
+    return [out[r * nmax: r * nmax + n] for r, n in enumerate(counts)]
+
+
+def _gather_rows(local: torch.Tensor, counts: List[int], group, dst: int) -> Optional[List[torch.Tensor]]:
+    """the same towards one rank: the list on `dst`, None elsewhere."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return [local]
+    nmax = max(counts) if counts else 0
+    send = _pad_rows(local, nmax)
+    bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, bufs, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+    return [b[:n] for b, n in zip(bufs, counts)] if rank == dst else None
 
 
 class ShardedCodec:
     """encode()/decode() of an `AudioCodec`, window-sharded over a process group."""
 
-    def __init__(self, model, group=None, encode_jobs: Optional[Callable] = None, decode_jobs: Optional[Callable] = None):
+    def __init__(self, model, group=None, encode_jobs: Optional[Callable] = None, decode_jobs: Optional[Callable] = None,
+                 dst: int = 0):
         self.model = model
         self.group = group
+        self.dst = dst
         self.encode_jobs = encode_jobs or model.encode_jobs
         self.decode_jobs = decode_jobs or model.decode_jobs
 
     @torch.inference_mode()
     def encode(self, wav_list, overlap_seconds=10, device=torch.device("cuda")):
+        """-> {"codes_list": ...} on every rank (codes are small; decode() needs them everywhere)."""
         m = self.model
         device = torch.device(device)
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
@@ -48,34 +75,52 @@ class ShardedCodec:
             return {"codes_list": [torch.zeros(m.num_groups, 0, device=device, dtype=torch.long) for _ in lens]}
         shards = windows.shard_round_robin(len(jobs), [j.n_valid for j in jobs], world)
         mine = self.encode_jobs(wav_list, [jobs[j] for j in shards[rank]], device)          # (8, n_r, 375)
-        rows = _gather_rows(mine.permute(1, 0, 2).contiguous(), [len(s) for s in shards], self.group)   # (N, 8, 375)
-        order = torch.tensor([j for s in shards for j in s], dtype=torch.int64, device=device)
+        parts = _all_gather_rows(mine.permute(1, 0, 2), [len(s) for s in shards], self.group)   # [(n_r, 8, 375)]
+        order = torch.tensor([j for s in shards for j in s], dtype=torch.int64).to(device, non_blocking=True)
+        rows = torch.cat(parts, dim=0) if len(parts) > 1 else parts[0]
         codes = torch.empty_like(rows)
-        codes[order] = rows                                                                    # back to job order
+        codes.index_copy_(0, order, rows)                                                      # back to job order
         return {"codes_list": m.stitch_codes(codes.permute(1, 0, 2).contiguous(), lens, jobs, overlap_seconds)}
 
     @torch.inference_mode()
-    def decode(self, codes_list, overlap_seconds=10, device=torch.device("cuda")):
+    def decode(self, codes_list, overlap_seconds=10, device=torch.device("cuda"), gather_wav: bool = True):
+        """-> {"syn_wav_list": ...}: the stitched waveforms on rank `dst` (None on the other ranks); with
+        gather_wav=False nothing is exchanged and every rank gets {"local": [(item, offset, samples tensor), ...]}."""
         m = self.model
         device = torch.device(device)
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         lens = [int(c.shape[-1]) for c in codes_list]
         up = m.decoder_upsample_rate
-        outs = [torch.zeros(L * up, dtype=torch.float32, device=device) for L in lens]
         groups = windows.plan_decode(lens, overlap_seconds, m.input_sample_rate, m.max_audio_seconds, m.encoder_downsample_rate)
+        keep_args = (overlap_seconds, m.input_sample_rate, m.max_audio_seconds, m.encoder_downsample_rate, up)
+        on_dst = rank == self.dst
+        outs = None
+        if gather_wav and on_dst:            # one flat buffer, one view per item: every sample is written by exactly one window
+            flat = torch.empty(sum(lens) * up, dtype=torch.float32, device=device)
+            outs = list(torch.split(flat, [L * up for L in lens]))
+        local, dst_views, src_views = [], [], []
         for pad_len, jobs in sorted(groups.items()):
             shards = windows.shard_round_robin(len(jobs), [j.n_valid for j in jobs], world)
             my_jobs = [jobs[j] for j in shards[rank]]
             if my_jobs:
                 wav = self.decode_jobs(codes_list, my_jobs, device)                         # (n_r, 1280 T')
             else:
-                wav = torch.zeros((0, up * pad_len), dtype=torch.float32, device=device)
-            rows = _gather_rows(wav, [len(s) for s in shards], self.group)
-            k = 0
-            for s in shards:
-                for j in s:
-                    off, n = windows.decode_keep(jobs[j], overlap_seconds, m.input_sample_rate, m.max_audio_seconds,
-                                                 m.encoder_downsample_rate, up)
-                    outs[jobs[j].item][off:off + n] = rows[k, :n]
-                    k += 1
+                wav = torch.empty((0, up * pad_len), dtype=torch.float32, device=device)
+            if not gather_wav:
+                for k, j in enumerate(my_jobs):
+                    off, n = windows.decode_keep(j, *keep_args)
+                    local.append((j.item, off, wav[k, :n]))
+                continue
+            parts = _gather_rows(wav, [len(s) for s in shards], self.group, self.dst)
+            if not on_dst:
+                continue
+            for r, s in enumerate(shards):
+                for k, j in enumerate(s):
+                    off, n = windows.decode_keep(jobs[j], *keep_args)
+                    dst_views.append(outs[jobs[j].item][off:off + n])
+                    src_views.append(parts[r][k, :n])
+        if not gather_wav:
+            return {"local": local}
+        if on_dst and dst_views:
+            torch._foreach_copy_(dst_views, src_views)                                          # one fused launch for all windows
         return {"syn_wav_list": outs}

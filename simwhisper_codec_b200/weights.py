@@ -206,9 +206,17 @@ def _uniform(rng: np.random.Generator, shape, bound: float) -> np.ndarray:
     return ((rng.random(shape) * 2.0 - 1.0) * bound).astype(np.float32)
 
 
+OUTLIER_CHANNELS = (41, 302, 577, 760)
+
+
 def random_state_dict(gp: dict, seed: int = 0, exercise: bool = True,
-                      latent_gain: float = 4.0) -> "OrderedDict[str, torch.Tensor]":
-    """Deterministic random-init state dict with the reference's key schema (CPU tensors)."""
+                      latent_gain: float = 4.0, outlier_gain: float = 0.0) -> "OrderedDict[str, torch.Tensor]":
+    """Deterministic random-init state dict with the reference's key schema (CPU tensors).
+
+    outlier_gain > 0: Whisper-like outlier stress.  Trained Whisper encoders carry a few residual-stream channels whose
+    magnitude is ~50x the rest; random init has none, so bf16 accuracy would only ever be tested on benign statistics.
+    The rows of every tensor that WRITES the 768-wide residual stream (conv2, out_proj, fc2 of both transformer stacks)
+    are scaled by `outlier_gain` for OUTLIER_CHANNELS, which puts those channels of h at ~gain x the others."""
     schema = state_dict_schema(gp)
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     arrays: Dict[str, np.ndarray] = {}
@@ -248,6 +256,16 @@ def random_state_dict(gp: dict, seed: int = 0, exercise: bool = True,
             if key == "downsample.to_latent.weight_g":
                 g = g * latent_gain
         arrays[key] = g.astype(np.float32)
+    if outlier_gain > 0:
+        ch = list(OUTLIER_CHANNELS)
+        for key in arrays:
+            leaf = key.split(".")
+            writes_h = (key == "acoustic_encoder.conv2.weight" or
+                        (leaf[0] in ("acoustic_encoder", "acoustic_decoder") and leaf[1] == "layers" and
+                         (leaf[3:5] == ["self_attn", "out_proj"] or leaf[3] == "fc2")))
+            if writes_h:
+                arrays[key] = arrays[key].copy()
+                arrays[key][ch] = arrays[key][ch] * np.float32(outlier_gain)
     for key, (shape, dtype, _) in schema.items():
         t = torch.from_numpy(np.ascontiguousarray(arrays[key]))
         assert tuple(t.shape) == tuple(shape) and t.dtype == dtype, (key, t.shape, t.dtype)

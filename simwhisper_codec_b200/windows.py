@@ -15,6 +15,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, List, Sequence, Tuple
 
+import numpy as np
+
 
 @dataclass(frozen=True)
 class EncodeJob:
@@ -44,21 +46,44 @@ def plan_encode(lens: Sequence[int], overlap_seconds: int = 10, sr: int = 16000,
     return jobs
 
 
+def code_frames(n_samples: int) -> int:
+    """Valid code frames of a window with n_samples valid samples: mel ceil(n/160) -> encoder //2 -> down-sampler ceil(/4)
+    (reference feature_extractor.py:221-226, modules.py:322, 549)."""
+    return (((n_samples + 159) // 160) // 2 + 3) // 4
+
+
 def encode_gather_index(lens: Sequence[int], jobs: Sequence[EncodeJob], overlap_seconds: int = 10, sr: int = 16000,
-                        max_seconds: int = 30, rate: int = 1280, frames_per_window: int = 375) -> Tuple[List[int], List[int]]:
-    """Flat source index (job * 375 + frame) of every output code position, and the per-item output lengths.
-    Output position p of item i comes from its window p // keep, frame p % keep; items keep len // rate codes."""
-    keep = (max_seconds - overlap_seconds) * sr // rate
-    first: Dict[int, int] = {}
+                        max_seconds: int = 30, rate: int = 1280, frames_per_window: int = 375) -> Tuple[np.ndarray, List[int]]:
+    """Flat source index (job * 375 + frame; int64 array) of every output code position, and the per-item output lengths.
+
+    The reference concatenates `keep` code columns per window index of the BATCH (model.py:271-302): output position p of
+    item i is frame p % keep of its window p // keep if the item owns that window and the frame is below the window's valid
+    code length, else zero (source index -1); an item keeps min(len // rate, max_chunks * keep) positions.  With the default
+    overlap (hop a multiple of `rate`) every position has a source; with e.g. overlap 5 s (hop 400 000 samples, keep 312) the
+    reference's time axis drifts and the trailing positions are zeros or cut - reproduced here as it is."""
+    hop = (max_seconds - overlap_seconds) * sr
+    keep = hop // rate
+    if keep <= 0 or not lens:
+        return np.zeros(0, np.int64), [0 for _ in lens]
+    max_chunks = (max(lens) + hop - 1) // hop
+    owned: Dict[Tuple[int, int], Tuple[int, int]] = {}     # (item, window index) -> (job index, valid code frames kept)
     for j, job in enumerate(jobs):
-        first.setdefault(job.item, j)
-    src: List[int] = []
+        owned[(job.item, job.start // hop)] = (j, min(code_frames(job.n_valid), keep))
     splits: List[int] = []
+    seg_len, seg_job, seg_valid = [], [], []                # one segment per (item, window index) of the output
     for i, L in enumerate(lens):
-        n = L // rate
+        n = min(L // rate, max_chunks * keep)
         splits.append(n)
-        base = first.get(i, 0)
-        src.extend((base + p // keep) * frames_per_window + p % keep for p in range(n))
+        for c in range((n + keep - 1) // keep):
+            j, valid = owned.get((i, c), (0, 0))
+            seg_len.append(min(keep, n - c * keep))
+            seg_job.append(j)
+            seg_valid.append(valid)
+    seg_len = np.asarray(seg_len, np.int64)
+    total = int(seg_len.sum())
+    frame = np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(seg_len) - seg_len, seg_len)
+    src = np.repeat(np.asarray(seg_job, np.int64), seg_len) * frames_per_window + frame
+    src[frame >= np.repeat(np.asarray(seg_valid, np.int64), seg_len)] = -1
     return src, splits
 
 

@@ -108,3 +108,34 @@ def test_api_batch_windows(sd_ex):
     assert snr_db(torch.from_numpy(g["wav1_seam"]), wav[1][310000:330000]) > 100
     assert snr_db(torch.from_numpy(g["wav1_tail"]), wav[1][-32000:]) > 100
     assert snr_db(torch.from_numpy(g["wav2_seam"]), wav[2][312000:328000]) > 100
+
+
+def test_encoder_hidden_states(sd_ex):
+    """output_hidden_states=True (reference modules.py:344-371) against the reference's own 13 tensors."""
+    g = load_golden("hidden_small_ex.npz")
+    f = load_golden("forward_small_ex.npz")
+    mel, lens = torch.from_numpy(f["mel"]), torch.from_numpy(f["mel_lens"])
+    with torch.inference_mode():
+        out, ol, hs = port.encoder(sd_ex, mel, lens, output_hidden_states=True)
+    assert len(hs) == 13 and ol.tolist() == g["out_len"].tolist()
+    assert torch.allclose(out[:, ::8], torch.from_numpy(g["out"]), atol=2e-6, rtol=0)
+    for i, h in enumerate(hs):
+        assert torch.allclose(h[:, ::8], torch.from_numpy(g["hidden"][i]), atol=5e-6, rtol=0), i
+    assert float(hs[3][1, :, 68:].abs().max()) == 0.0           # item 1 has 137 // 2 = 68 valid tokens: the rest is masked
+
+
+def test_outlier_weights_forward(gen_params):
+    """Whisper-like outlier-channel weights: the port follows the reference there too (fp32 vs fp32)."""
+    g = load_golden("outlier_ex.npz")
+    sd = W.random_state_dict(gen_params, seed=0, exercise=True, outlier_gain=50.0)
+    assert W.state_dict_digest(sd) == str(g["digest"])
+    mel, lens = torch.from_numpy(g["mel"]), torch.from_numpy(g["mel_lens"])
+    with torch.inference_mode():
+        enc, el = port.encoder(sd, mel, lens)
+        lat, ll = port.downsample(sd, enc, el)
+        zq, codes = port.fsq_encode(lat, ll)
+    assert torch.allclose(enc, torch.from_numpy(g["enc"]), atol=2e-5, rtol=0)
+    flips = (codes != torch.from_numpy(g["codes"])).float().mean()
+    assert float(flips) < 1e-3, float(flips)
+    rms = g["channel_rms"]
+    assert rms[list(W.OUTLIER_CHANNELS)].min() > 20 * np.median(rms)      # the stress is what it says: >20x outlier channels

@@ -30,7 +30,10 @@ class FakeCodec:
 
     def stitch_codes(self, codes, lens, jobs, overlap_seconds):
         src, splits = windows.encode_gather_index(lens, jobs, overlap_seconds)
-        return list(torch.split(codes.reshape(8, -1).index_select(1, torch.tensor(src, dtype=torch.int64)), splits, dim=1))
+        flat = torch.cat([codes.reshape(8, -1), torch.zeros(8, 1, dtype=codes.dtype)], dim=1)      # last column: the zero source
+        src = torch.from_numpy(src)
+        src = torch.where(src < 0, torch.full_like(src, flat.shape[1] - 1), src)
+        return list(torch.split(flat.index_select(1, src), splits, dim=1))
 
     def decode_jobs(self, codes_list, jobs, device):
         Tp = jobs[0].pad_len
@@ -73,6 +76,57 @@ def test_encode_plan_matches_reference_loop():
     ref = _reference_style_encode(fake, wavs)
     assert [tuple(c.shape) for c in ours] == [(8, n // 1280) for n in lens]
     for a, b in zip(ours, ref):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("overlap", [0, 5, 10, 25])
+def test_encode_plan_matches_reference_loop_any_overlap(overlap):
+    """hop not a multiple of 1280 (overlap 5 -> keep 312, overlap 25 -> keep 62): the reference's code axis drifts against
+    the sample axis, trailing positions are zero or cut (model.py:271-302) - the flat plan reproduces exactly that."""
+    g = torch.Generator().manual_seed(overlap)
+    for lens in ([1200000], [48123, 800000, 365000, 1280 * 250, 479999, 1279], [400000, 400001, 399999, 1600000]):
+        wavs = [torch.randn(n, generator=g) for n in lens]
+        fake = FakeCodec()
+        jobs = windows.plan_encode(lens, overlap)
+        ours = fake.stitch_codes(fake.encode_jobs(wavs, jobs, "cpu"), lens, jobs, overlap)
+        ref = _reference_style_encode(fake, wavs, overlap)
+        assert [tuple(c.shape) for c in ours] == [tuple(c.shape) for c in ref]
+        for a, b in zip(ours, ref):
+            assert torch.equal(a, b)
+
+
+def _reference_style_decode(fake, codes_list, overlap):
+    """the reference's decode chunk loop (model.py:320-367) around the same fake compute"""
+    keep, win = (30 - overlap) * 16000 // 1280, 375
+    L = [c.shape[-1] for c in codes_list]
+    maxlen = max(L)
+    pieces = []
+    for c in range((maxlen + keep - 1) // keep):
+        s, e = c * keep, min(c * keep + win, maxlen)
+        jobs = [windows.DecodeJob(i, c, s, max(0, min(L[i] - s, e - s)), e - s) for i in range(len(L))]
+        wav = fake.decode_jobs(codes_list, jobs, "cpu")
+        piece = torch.zeros(len(L), keep * 1280)
+        for b, j in enumerate(jobs):
+            v = min(j.n_valid, keep) * 1280
+            piece[b, :v] = wav[b, :v]
+        pieces.append(piece)
+    allw = torch.cat(pieces, -1)
+    return [allw[i, : L[i] * 1280] for i in range(len(L))]
+
+
+@pytest.mark.parametrize("overlap", [0, 5, 10, 25])
+def test_decode_plan_matches_reference_loop_any_overlap(overlap):
+    g = torch.Generator().manual_seed(100 + overlap)
+    fake = FakeCodec()
+    codes_list = [torch.randint(0, 2016, (8, n), generator=g) for n in (37, 625, 285, 936, 1)]
+    L = [c.shape[-1] for c in codes_list]
+    outs = [torch.zeros(n * 1280) for n in L]
+    for _, dj in windows.plan_decode(L, overlap).items():
+        w = fake.decode_jobs(codes_list, dj, "cpu")
+        for k, j in enumerate(dj):
+            off, n = windows.decode_keep(j, overlap)
+            outs[j.item][off:off + n] = w[k, :n]
+    for a, b in zip(outs, _reference_style_decode(fake, codes_list, overlap)):
         assert torch.equal(a, b)
 
 

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Phase timeline of one persistent CTA of the tcgen05 attention kernel (clock64 stamps of the first softmax warp of query
 tile 0): A item decoded | per key block: B S ready, C P handed over | D last P V done | E item stored.
-`--fine` for a library built with -DSWC_ATTN_FINE_TRACE (four more stamps per key block; they perturb the kernel by ~20 %)."""
+`--fine`: four more stamps per key block (they perturb the kernel by ~20 %).  Both query tiles are traced; the raw stamps go
+to gpurun_out/attn_trace.npy when that directory exists."""
 import ctypes as C
 import os
 import sys
@@ -32,18 +33,26 @@ def main():
                                           B, T, H, st), "attention")
     run()
     torch.cuda.synchronize()
-    assert fn(1, None, 0) == 0
+    fine = "--fine" in sys.argv
+    assert fn(3 if fine else 1, None, 0) == 0
     run()
     buf = np.zeros(3 * 4096, dtype=np.int64)
     assert fn(0, buf.ctypes.data, buf.size) == 0
-    t = buf[:4096]
-    t = t[t > 0]
+    if os.path.isdir("gpurun_out"):
+        np.save("gpurun_out/attn_trace.npy", buf)
     n_kt = 12
-    # the default build stamps B (S ready) and C (P handed over) per key block; a library built with
-    # -DSWC_ATTN_FINE_TRACE adds B1 (S in registers), B2 (row maximum known), B3 (exponentials done), B4 (previous P V done)
-    fine = "--fine" in sys.argv
     k = 6 if fine else 2
     per = 1 + k * n_kt + 2
+    t0, t1 = buf[:4096], buf[4096:8192]
+    n = min((t0 > 0).sum(), (t1 > 0).sum()) // per
+    b0 = t0[: n * per].reshape(n, per)[:, 1:1 + k * n_kt].reshape(n, n_kt, k)[:, :, 0]
+    b1 = t1[: n * per].reshape(n, per)[:, 1:1 + k * n_kt].reshape(n, n_kt, k)[:, :, 0]
+    print("tile 1 'S ready' minus tile 0 'S ready', per key block of item 3:", (b1[3] - b0[3]).tolist())
+    print("median offset over items 2..:", int(np.median((b1 - b0)[2:])))
+    t = buf[:4096]
+    t = t[t > 0]
+    # the default build stamps B (S ready) and C (P handed over) per key block; a library built with
+    # -DSWC_ATTN_FINE_TRACE adds B1 (S in registers), B2 (row maximum known), B3 (exponentials done), B4 (previous P V done)
     items = len(t) // per
     t = t[: items * per].reshape(items, per)
     A, D, E = t[:, 0], t[:, -2], t[:, -1]
