@@ -463,13 +463,28 @@ int swc_test_gemm(int backend, const void* A, const void* W, const float* bias, 
 void swc_set_gemm_variant(int variant) { set_gemm_variant(variant); }
 
 int swc_test_attention(int backend, const void* qkv, void* out, const int64_t* lens, int batch, int T, int heads, void* stream) {
-  if (backend == 0) return attention_simt(qkv, 0, out, (const long long*)lens, batch, T, heads, (cudaStream_t)stream);
-  if (backend == 1) return attention_simt(qkv, 1, out, (const long long*)lens, batch, T, heads, (cudaStream_t)stream);
-  if (backend == 2) return attention_mma((const bf16*)qkv, (bf16*)out, (const long long*)lens, batch, T, heads, (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (backend == 0) return attention_simt(qkv, 0, out, (const long long*)lens, batch, T, heads, s);
+  if (backend == 1) return attention_simt(qkv, 1, out, (const long long*)lens, batch, T, heads, s);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return attention_tc((const bf16*)qkv, (bf16*)out, (const long long*)lens, batch, T, heads, sms, (cudaStream_t)stream);
+  if (backend == 2) {
+    // bf16x3 tcgen05 kernel behind an fp32 interface: split qkv into (hi | lo) planes, run, merge the output planes
+    const long long rows = (long long)batch * T;
+    const int D = heads * 64;
+    bf16 *pin = nullptr, *pout = nullptr;
+    SWC_CHECK_CUDA(cudaMalloc(&pin, (size_t)rows * 6 * D * sizeof(bf16)));
+    SWC_CHECK_CUDA(cudaMalloc(&pout, (size_t)rows * 2 * D * sizeof(bf16)));
+    int rc = split_bf16_planes((const float*)qkv, 3 * D, (long long)T * 3 * D, batch, T, 3 * D, pin, s);
+    if (rc == 0) rc = attention_tc_x3(pin, pout, (const long long*)lens, batch, T, heads, sms, s);
+    if (rc == 0) rc = merge_bf16_planes(pout, rows, D, (float*)out, s);
+    cudaStreamSynchronize(s);
+    cudaFree(pin);
+    cudaFree(pout);
+    return rc;
+  }
+  return attention_tc((const bf16*)qkv, (bf16*)out, (const long long*)lens, batch, T, heads, sms, s);
 }
 
 }  // extern "C"

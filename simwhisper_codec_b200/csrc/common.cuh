@@ -94,6 +94,31 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// bf16x3 mode: values leave a kernel as two bf16 planes, x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (2^-17 relative):
+// hi at p[0..n), lo at p[plane_stride + 0..n).  Same arithmetic as split_bf16_planes (kernels.cu), so a producer that
+// writes planes directly is bit-identical to writing fp32 and splitting afterwards.
+struct bf16_planes {};      // output-type tag of the row-wise kernels: rows of (hi | lo) planes, C columns each
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void store8_planes(bf16* p, long long plane_stride, const float (&v)[8]) {
+  uint4 h, l;
+  split_pair(v[0], v[1], h.x, l.x); split_pair(v[2], v[3], h.y, l.y);
+  split_pair(v[4], v[5], h.z, l.z); split_pair(v[6], v[7], h.w, l.w);
+  *reinterpret_cast<uint4*>(p) = h;
+  *reinterpret_cast<uint4*>(p + plane_stride) = l;
+}
+__device__ __forceinline__ void store4_planes(bf16* p, long long plane_stride, float4 v) {
+  uint2 h, l;
+  split_pair(v.x, v.y, h.x, l.x); split_pair(v.z, v.w, h.y, l.y);
+  *reinterpret_cast<uint2*>(p) = h;
+  *reinterpret_cast<uint2*>(p + plane_stride) = l;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

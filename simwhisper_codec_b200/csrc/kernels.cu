@@ -3,6 +3,8 @@
 // kernels: coalesced along the channel (contiguous) dimension, 16/32-byte vector accesses, fp32 math.
 #include <algorithm>
 
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace swc {
@@ -17,11 +19,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, float eps, int nb,
                                                         int t_in, int t_out, const long long* __restrict__ lens) {
   constexpr int C = NCH * 256;
+  constexpr bool kPlanes = std::is_same<TO, bf16_planes>::value;     // rows of (hi | lo) bf16 planes, C columns each
+  using TE = typename std::conditional<kPlanes, bf16, TO>::type;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (long long)nb * t_out) return;
   const int b = (int)((unsigned)row / (unsigned)t_out), t = (int)row - b * t_out;     // nb * t_out < 2^31 (checked by the launcher)
-  TO* o = out + row * C;
+  TE* o = reinterpret_cast<TE*>(out) + row * (kPlanes ? 2 * C : C);
   const bool in_range = t < t_in;
   // the length is fetched together with the row, not before it: a row load that waits for lens[b] pays the L2 latency
   // twice (rows beyond the length are then read for nothing; variable-length batches run the packed path instead)
@@ -46,7 +50,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   if (!live) {
     float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) store8(o + (c * 32 + lane) * 8, z);
+    for (int c = 0; c < NCH; ++c) {
+      store8(o + (c * 32 + lane) * 8, z);
+      if constexpr (kPlanes) store8(o + C + (c * 32 + lane) * 8, z);
+    }
     return;
   }
   float sum = 0.f;
@@ -69,7 +76,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     load8(beta + c0, bt);
 #pragma unroll
     for (int j = 0; j < 8; ++j) r[j] = (v[c][j] - mean) * rstd * g[j] + bt[j];
-    store8(o + c0, r);
+    if constexpr (kPlanes) store8_planes(o + c0, C, r);
+    else store8(o + c0, r);
   }
 }
 
@@ -91,6 +99,7 @@ static int layernorm_t(const float* in, const float* delta, float* h_out, void* 
 int layernorm(const float* in, const float* delta, float* h_out, void* out, int out_type, const float* gamma,
               const float* beta, float eps, int nb, int t_in, int t_out, int C, const long long* lens, cudaStream_t s) {
   if (out_type == 0) return layernorm_t<float>(in, delta, h_out, out, gamma, beta, eps, nb, t_in, t_out, C, lens, s);
+  if (out_type == 2) return layernorm_t<bf16_planes>(in, delta, h_out, out, gamma, beta, eps, nb, t_in, t_out, C, lens, s);
   return layernorm_t<bf16>(in, delta, h_out, out, gamma, beta, eps, nb, t_in, t_out, C, lens, s);
 }
 
@@ -185,6 +194,8 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
                                                                    const float* __restrict__ beta, float eps,
                                                                    TO* __restrict__ out, int T, int strip) {
   constexpr int C = 512, R = kDwRows;
+  constexpr bool kPlanes = std::is_same<TO, bf16_planes>::value;     // rows of (hi | lo) bf16 planes (bf16x3 mode: exact rstd)
+  using TE = typename std::conditional<kPlanes, bf16, TO>::type;
   __shared__ __align__(16) float red_sum[R][4];
   __shared__ __align__(16) float red_sq[R][4];
   __shared__ __align__(16) float sw[7 * C];            // taps: read back per step instead of living in 28 registers
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
   const float* xb = x + (long long)b * T * C + c0;
   const float* db = HAS_DELTA ? delta + (long long)b * T * C + c0 : nullptr;
   float* xo = HAS_DELTA ? x_out + (long long)b * T * C + c0 : nullptr;
-  TO* ob = out + (long long)b * T * C + c0;
+  TE* ob = reinterpret_cast<TE*>(out) + (long long)b * T * (kPlanes ? 2 * C : C) + c0;
 
 #pragma unroll
   for (int k = 0; k < 7; ++k) *reinterpret_cast<float4*>(sw + k * C + c0) = *reinterpret_cast<const float4*>(w + k * C + c0);
@@ -290,7 +301,9 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
       if (t < t_end) {
         const float4 p = *reinterpret_cast<const float4*>(red_sq[r]);
         const float rstd = dw_rstd<TO>(((p.x + p.y) + (p.z + p.w)) * (1.0f / C) + eps);
-        store4(ob + (long long)t * C, f4(fma(mul(y[r], f4p(rstd)), gmp, btp)));
+        const float4 res = f4(fma(mul(y[r], f4p(rstd)), gmp, btp));
+        if constexpr (kPlanes) store4_planes(ob + (long long)t * 2 * C, C, res);
+        else store4(ob + (long long)t * C, res);
       }
     }
   }
@@ -304,7 +317,10 @@ int dwconv7_ln(const float* x, const float* delta, float* x_out, const float* w7
   // strips of 64 rows (9 % halo re-reads, served by the L2) when that gives every SM many blocks, else 32
   const int strip = ((long long)nb * ceil_div(T, 64) >= 16 * 148) ? 64 : 32;
   dim3 grid(ceil_div(T, strip), nb);
-  if (out_type == 0) {
+  if (out_type == 2) {
+    if (delta) dwconv7_ln_kernel<bf16_planes, true><<<grid, kDwThreads, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (bf16_planes*)out, T, strip);
+    else dwconv7_ln_kernel<bf16_planes, false><<<grid, kDwThreads, 0, s>>>(x, nullptr, nullptr, w7c, bias, gamma, beta, eps, (bf16_planes*)out, T, strip);
+  } else if (out_type == 0) {
     if (delta) dwconv7_ln_kernel<float, true><<<grid, kDwThreads, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (float*)out, T, strip);
     else dwconv7_ln_kernel<float, false><<<grid, kDwThreads, 0, s>>>(x, nullptr, nullptr, w7c, bias, gamma, beta, eps, (float*)out, T, strip);
   } else {
@@ -720,6 +736,23 @@ int split_bf16_planes(const float* in, long long row_stride, long long batch_str
   if (total == 0) return 0;
   ProfScope ps(KC_MISC, s);
   split_bf16_planes_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, s>>>(in, row_stride, batch_stride, rows, cols / 8, planes, total);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// planes (rows, hi cols | lo cols) bf16 -> fp32 rows (hi + lo): the inverse view, used by the test entry points
+__global__ void __launch_bounds__(256) merge_bf16_planes_kernel(const bf16* __restrict__ planes, float* __restrict__ out, int cols, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long r = i / cols;
+  const int c = (int)(i - r * cols);
+  out[i] = __bfloat162float(planes[r * 2 * cols + c]) + __bfloat162float(planes[r * 2 * cols + cols + c]);
+}
+int merge_bf16_planes(const bf16* planes, long long rows, int cols, float* out, cudaStream_t s) {
+  const long long total = rows * cols;
+  if (total == 0) return 0;
+  ProfScope ps(KC_MISC, s);
+  merge_bf16_planes_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, s>>>(planes, out, cols, total);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

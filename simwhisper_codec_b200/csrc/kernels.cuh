@@ -54,6 +54,9 @@ constexpr int kMaxRagged = 256;      // items per ragged call: the table travels
 int split_bf16_planes(const float* in, long long row_stride, long long batch_stride, int nb, int rows, int cols, bf16* planes,
                       cudaStream_t s);
 
+// (rows, hi | lo) bf16 planes of `cols` columns each -> fp32 rows hi + lo
+int merge_bf16_planes(const bf16* planes, long long rows, int cols, float* out, cudaStream_t s);
+
 struct RaggedTable {          // passed by value to kernels (2 KB)
   int nb = 0;
   int t_max = 0;              // longest item
@@ -68,12 +71,11 @@ int unpack_rows(const void* packed, void* padded, int dtype, const RaggedTable& 
 
 // fp32 SIMT flash attention over fused qkv rows (nb*T, 3*H*64): q pre-scaled. Keys >= lens[b] masked.
 int attention_simt(const void* qkv, int type, void* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
-// bf16x3 mode: fp32-class flash attention on mma.sync over the (hi | lo) bf16 planes of the fp32 qkv rows, fp32 output
-int attention_mma_x3(const bf16* planes, float* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
+// bf16x3 mode: fp32-class flash attention on tcgen05 (attention_tc_x3.cu) over the (hi | lo) bf16 planes of the fp32 qkv rows
+// (rows of 2 x 3*H*64 bf16); the output rows are (hi | lo) planes of H*64 columns each — the operand of the out_proj GEMM
+int attention_tc_x3(const bf16* planes, bf16* out_planes, const long long* lens, int nb, int T, int H, int num_sms, cudaStream_t s);
 // the same over packed rows (planes and out hold tab.total rows; item b = rows [off[b], off[b] + len[b]))
-int attention_mma_x3_ragged(const bf16* planes, float* out, const RaggedTable& tab, int H, cudaStream_t s);
-// bf16 tensor-core flash attention (mma.sync m16n8k16), same contract
-int attention_mma(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
+int attention_tc_x3_ragged(const bf16* planes, bf16* out_planes, const RaggedTable& tab, int H, int num_sms, cudaStream_t s);
 // bf16 flash attention on tcgen05 / TMEM / TMA (attention_tc.cu), same contract
 int attention_tc(const bf16* qkv, bf16* out, const long long* lens, int nb, int T, int H, int num_sms, cudaStream_t s);
 // the same kernel over packed rows: item b owns rows [off[b], off[b] + len[b]) of qkv / out; no padded rows exist

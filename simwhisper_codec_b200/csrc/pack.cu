@@ -391,9 +391,14 @@ int upload_model(Model& m, int device) {
   m.num_sms = prop.multiProcessorCount;
   m.device = device;
   const bool bf = m.precision == 1;
+  // stored as bf16: every GEMM operand in bf16 mode; in bf16x3 mode only the two pre-split DFT operands (their entries are
+  // bf16-exact terms w1, w2, w3 of the fp32 tables, consumed by the plain tensor-core GEMM)
+  auto as_bf16 = [&](const std::string& name, const Packed& p) {
+    return p.as_act_type && (bf || (m.x3() && (name == "mel.dft.w6" || name == "voc.idft.w3")));
+  };
   size_t total = 0;
   for (auto& kv : m.tab) {
-    const size_t bytes = kv.second.host.size() * ((kv.second.as_act_type && bf) ? 2 : 4);
+    const size_t bytes = kv.second.host.size() * (as_bf16(kv.first, kv.second) ? 2 : 4);
     total += (bytes + 255) / 256 * 256;
   }
   char* slab = nullptr;
@@ -405,7 +410,7 @@ int upload_model(Model& m, int device) {
     if (kv.first == "__slab__") continue;
     Packed& p = kv.second;
     p.dev = slab + off;
-    if (p.as_act_type && bf) {
+    if (as_bf16(kv.first, p)) {
       tmp.resize(p.host.size());
       for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = f32_to_bf16_rn(p.host[i]);
       SWC_CHECK_CUDA(cudaMemcpy(p.dev, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice));

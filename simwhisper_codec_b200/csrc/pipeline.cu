@@ -53,6 +53,12 @@ bool x3_planes(const Ctx& c, const LinearW& a, const LinearW& b) {
          a.N >= 256 && a.K % 64 == 0 && b.K == a.N;
 }
 
+// bf16x3 mode: may a row-wise producer (LayerNorm, dwconv + LayerNorm) write its result directly as the (hi | lo) planes
+// the three-product GEMM `w` reads?  (Same arithmetic as the split pass it replaces: bit-identical results.)
+bool x3_rowwise_planes(const Ctx& c, const LinearW& w) {
+  return c.m->x3() && !c.force_simt && w.w3 != nullptr && w.K % 64 == 0 && w.N % 8 == 0;
+}
+
 // dispatch on the model precision: bf16 operands go to the tcgen05 kernel, fp32 to the SIMT kernel.
 // bf16x3 mode (fp32 activations): the fp32 operand is split into two bf16 planes (hi | lo) and the contraction runs on the
 // tensor cores as three products a_hi w_hi + a_hi w_lo + a_lo w_hi with fp32 accumulation: every tap of the problem
@@ -91,26 +97,16 @@ int run_gemm(Ctx& c, const GemmDesc& d, int kind, int a_type, int out_type) {
   return gemm_simt(d, kind, a_type, out_type, c.s);
 }
 
-int run_attention(Ctx& c, const void* qkv, void* out, const long long* lens, int nb, int T, bool qkv_planes = false) {
+// bf16 mode: bf16 rows in and out (tcgen05).  bf16x3 mode with the qkv planes of the pair GEMM: the three-product tcgen05
+// kernel, whose output is again (hi | lo) planes (`*out_planes` = true).  Otherwise fp32 SIMT.
+int run_attention(Ctx& c, const void* qkv, void* out, const long long* lens, int nb, int T, bool qkv_planes, bool* out_planes) {
+  *out_planes = false;
   if (c.dry) return 0;
   const int at = c.m->act_type();
-  if (at == 1 && !c.force_simt) {
-    static const bool use_mma = [] { const char* e = getenv("SWC_ATTENTION"); return e && e[0] == 'm'; }();   // "mma": legacy path
-    if (use_mma) return attention_mma((const bf16*)qkv, (bf16*)out, lens, nb, T, c.m->heads, c.s);
-    return attention_tc((const bf16*)qkv, (bf16*)out, lens, nb, T, c.m->heads, c.m->num_sms, c.s);
-  }
-  if (c.m->x3() && !c.force_simt) {
-    // bf16x3 mode: split the fp32 qkv rows into bf16 planes (same byte size), then the three-product mma.sync kernel
-    // (the qkv GEMM hands the planes over directly when it ran on the pair kernel: qkv_planes)
-    if (qkv_planes) return attention_mma_x3((const bf16*)qkv, (float*)out, lens, nb, T, c.m->heads, c.s);
-    const int D3 = 3 * c.m->heads * 64;
-    const size_t mark = c.ws.mark();
-    bf16* planes = (bf16*)c.ws.alloc((long long)nb * T * D3 * 4);
-    SWC_TRY(c.ws.check());
-    int rc = split_bf16_planes((const float*)qkv, D3, (long long)T * D3, nb, T, D3, planes, c.s);
-    if (rc == 0) rc = attention_mma_x3(planes, (float*)out, lens, nb, T, c.m->heads, c.s);
-    c.ws.release(mark);
-    return rc;
+  if (at == 1 && !c.force_simt) return attention_tc((const bf16*)qkv, (bf16*)out, lens, nb, T, c.m->heads, c.m->num_sms, c.s);
+  if (c.m->x3() && !c.force_simt && qkv_planes) {
+    *out_planes = true;
+    return attention_tc_x3((const bf16*)qkv, (bf16*)out, lens, nb, T, c.m->heads, c.m->num_sms, c.s);
   }
   return attention_simt(qkv, at, out, lens, nb, T, c.m->heads, c.s);
 }
@@ -144,33 +140,40 @@ int transformer_stack(Ctx& c, const std::vector<LayerW>& layers, float* h, const
     const bool qkv_planes = c.m->x3() && !c.force_simt && L.qkv.w3 != nullptr && get_gemm_variant() == 2;
     if (c.hidden_out && !rag)      // the layer's input, masked and channels-first
       SWC_TRY(cl_to_cf(h, 0, c.hidden_out + (long long)li * nb * D * T, nb, D, T, (long long)T * D, D, c.s, lens));
-    SWC_TRY(layernorm(h, nullptr, nullptr, xn, at, L.ln1_g, L.ln1_b, 1e-5f, nb, T, T, D, nullptr, c.s));
+    const bool xn1_planes = x3_rowwise_planes(c, L.qkv);
+    SWC_TRY(layernorm(h, nullptr, nullptr, xn, xn1_planes ? 2 : at, L.ln1_g, L.ln1_b, 1e-5f, nb, T, T, D, nullptr, c.s));
     {
-      GemmDesc d = base_desc(xn, D, 0, (int)rows, D, (int)rows, 1, L.qkv);
+      GemmDesc d = base_desc(xn, xn1_planes ? 2 * D : D, 0, (int)rows, D, (int)rows, 1, L.qkv);
+      d.a_planes = xn1_planes;
       set_out(d, qkv, qkv_planes ? 6 * D : 3 * D, 0);
       d.epi.out_planes = qkv_planes;
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, qkv_planes ? 1 : at));
     }
+    bool ao_planes = false;      // bf16x3: the attention output is already the (hi | lo) operand of the out_proj GEMM
     if (rag && m.x3()) {
       SWC_REQUIRE(qkv_planes, "bf16x3: the packed-token path needs the pair kernel's planes epilogue for qkv");
-      SWC_TRY(attention_mma_x3_ragged((const bf16*)qkv, (float*)ao, *rag, m.heads, c.s));
+      SWC_TRY(attention_tc_x3_ragged((const bf16*)qkv, (bf16*)ao, *rag, m.heads, m.num_sms, c.s));
+      ao_planes = true;
     } else if (rag) {
       SWC_TRY(attention_tc_ragged((const bf16*)qkv, (bf16*)ao, *rag, m.heads, m.num_sms, c.s));
     } else {
-      SWC_TRY(run_attention(c, qkv, ao, lens, nb, T, qkv_planes));
+      SWC_TRY(run_attention(c, qkv, ao, lens, nb, T, qkv_planes, &ao_planes));
     }
     {
-      GemmDesc d = base_desc(ao, D, 0, (int)rows, D, (int)rows, 1, L.out);
+      GemmDesc d = base_desc(ao, ao_planes ? 2 * D : D, 0, (int)rows, D, (int)rows, 1, L.out);
+      d.a_planes = ao_planes;
       set_out(d, h, D, 0);
       d.epi.residual = h; d.epi.res_row_stride = D;
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
     }
-    SWC_TRY(layernorm(h, nullptr, nullptr, xn, at, L.ln2_g, L.ln2_b, 1e-5f, nb, T, T, D, nullptr, c.s));
+    const bool xn2_planes = x3_rowwise_planes(c, L.fc1);
+    SWC_TRY(layernorm(h, nullptr, nullptr, xn, xn2_planes ? 2 : at, L.ln2_g, L.ln2_b, 1e-5f, nb, T, T, D, nullptr, c.s));
     // bf16x3 mode: fc1 hands its GELU output to fc2 as the two bf16 planes fc2's three-product GEMM reads (same bytes as
     // the fp32 hidden, no separate split pass over the widest operand of the layer)
     const bool planes = x3_planes(c, L.fc1, L.fc2);
     {
-      GemmDesc d = base_desc(xn, D, 0, (int)rows, D, (int)rows, 1, L.fc1);
+      GemmDesc d = base_desc(xn, xn2_planes ? 2 * D : D, 0, (int)rows, D, (int)rows, 1, L.fc1);
+      d.a_planes = xn2_planes;
       set_out(d, ff, planes ? 2 * m.ffn : m.ffn, 0);
       d.epi.act = gelu;
       d.epi.out_planes = planes;
@@ -419,10 +422,12 @@ int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav, int Tv_in, 
     }
     SWC_TRY(layernorm(e, nullptr, nullptr, x, 0, m.voc_norm_g, m.voc_norm_b, 1e-6f, nb, Tv, Tv, V, nullptr, c.s));
     for (const VocosBlockW& B : m.voc_blocks) {
-      SWC_TRY(dwconv7_ln(x, nullptr, nullptr, B.dw_w, B.dw_b, B.ln_g, B.ln_b, 1e-6f, y, at, nb, Tv, V, c.s));
+      const bool y_planes = x3_rowwise_planes(c, B.pw1);
+      SWC_TRY(dwconv7_ln(x, nullptr, nullptr, B.dw_w, B.dw_b, B.ln_g, B.ln_b, 1e-6f, y, y_planes ? 2 : at, nb, Tv, V, c.s));
       const bool planes = x3_planes(c, B.pw1, B.pw2);      // bf16x3 mode: the 4096-wide hidden goes to pwconv2 as bf16 planes
       {
-        GemmDesc d = base_desc(y, V, 0, (int)rows, V, (int)rows, 1, B.pw1);
+        GemmDesc d = base_desc(y, y_planes ? 2 * V : V, 0, (int)rows, V, (int)rows, 1, B.pw1);
+        d.a_planes = y_planes;
         set_out(d, g, planes ? 2 * I : I, 0);
         d.epi.act = at == 1 ? 2 : 1;
         d.epi.out_planes = planes;
@@ -440,7 +445,7 @@ int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav, int Tv_in, 
     SWC_TRY(layernorm(x, nullptr, nullptr, y, at, m.voc_final_g, m.voc_final_b, 1e-6f, nb, Tv, Tv, V, nullptr, c.s));
     float* S = (float*)region;
     float* frames = S + rows * NP;
-    const bool tc_idft = at == 1 && !c.force_simt && m.w_idft3 != nullptr;
+    const bool tc_idft = (at == 1 || m.x3()) && !c.force_simt && m.w_idft3 != nullptr;
     {   // head GEMM with exp/clip/sincos epilogue -> interleaved complex spectrum (fp32, or split bf16 planes s1|s2)
       GemmDesc d = base_desc(y, V, 0, (int)rows, V, (int)rows, 1, m.voc_head);
       set_out(d, S, NP, 0);
@@ -480,8 +485,8 @@ int mel_frontend(Ctx& c, const float* wav, long long wav_stride, int wav_cols, c
   float* power = (float*)c.ws.alloc((long long)nb * 3000 * 208 * 4);
   float* logmel = (float*)c.ws.alloc((long long)nb * 3000 * 80 * 4);
   float* item_max = (float*)c.ws.alloc((long long)nb * 4);
-  const bool tc_dft = m.act_type() == 1 && !c.force_simt && m.w_dft6 != nullptr;
-  bf16* frames = (m.act_type() == 1) ? (bf16*)c.ws.alloc((long long)nb * 3000 * 3 * 448 * 2) : nullptr;
+  const bool tc_dft = (m.act_type() == 1 || m.x3()) && !c.force_simt && m.w_dft6 != nullptr;
+  bf16* frames = (m.act_type() == 1 || m.x3()) ? (bf16*)c.ws.alloc((long long)nb * 3000 * 3 * 448 * 2) : nullptr;
   SWC_TRY(c.ws.check());
   if (!c.dry) {
     SWC_TRY(mel_pad(wav, wav_stride, wav_cols, lens, nb, padded, mel_lens, item_max, c.s));

@@ -78,12 +78,13 @@ def _attn_ref(qkv, lens, H):
     return o * ok[..., None]
 
 
-@pytest.mark.parametrize("backend,dtype,tol", [(0, torch.float32, 2e-5), (1, torch.bfloat16, 2e-2), (2, torch.bfloat16, 2e-2),
+@pytest.mark.parametrize("backend,dtype,tol", [(0, torch.float32, 2e-5), (1, torch.bfloat16, 2e-2), (2, torch.float32, 2e-5),
                                                 (3, torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("B,T,lens", [(2, 100, [100, 37]), (3, 257, [257, 1, 130]), (1, 1500, [1500]), (2, 375, [64, 375]),
                                       (3, 1500, [1500, 129, 700])])
 def test_attention(backend, dtype, tol, B, T, lens):
-    """backend 3 = tcgen05/TMEM flash attention (the product path in bf16 mode), 2 = legacy mma.sync kernel."""
+    """backend 3 = tcgen05/TMEM flash attention (the product path in bf16 mode), 2 = the three-product tcgen05 kernel of the
+    bf16x3 mode behind an fp32 interface (held to the fp32 kernel's tolerance), 0 / 1 = SIMT fp32 / bf16."""
     lib = _lib.load()
     H = 12
     g = torch.Generator(device="cuda").manual_seed(T)
@@ -111,15 +112,16 @@ def test_attention_growing_maximum(backend):
     ramp = torch.linspace(0.0, 6.0, T, device="cuda")
     qkv[..., H * 64: 2 * H * 64] += ramp[None, :, None] * 0.3          # keys drift along time
     qkv[..., : H * 64] = qkv[..., : H * 64].abs() * 0.4                # positive queries -> scores grow with the key index
-    qkv = qkv.bfloat16()
+    dtype, tol = (torch.float32, 2e-5) if backend == 2 else (torch.bfloat16, 2e-2)
+    qkv = qkv.to(dtype)
     lens_t = torch.tensor([T, 333], device="cuda", dtype=torch.int64)
-    out = torch.full((B, T, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out = torch.full((B, T, H * 64), float("nan"), device="cuda", dtype=dtype)
     _lib.check(lib.swc_test_attention(backend, _p(qkv), _p(out), _p(lens_t), B, T, H, _stream()), "attention")
     torch.cuda.synchronize()
     ref = _attn_ref(qkv, lens_t, H)
     ok = torch.arange(T, device="cuda")[None, :] < lens_t[:, None]
     diff = ((out.double() - ref) * ok[..., None]).abs().max().item()
-    assert diff < 2e-2, diff
+    assert diff < tol, diff
 
 
 @pytest.mark.parametrize("backend", [2, 3])
@@ -133,9 +135,10 @@ def test_attention_many_items_mixed_lengths(backend):
     lens[:8] = torch.tensor([1500, 1, 0, 128, 129, 256, 257, 1407])
     qkv = torch.randn(B, T, 3 * H * 64, generator=g) * 0.7
     qkv[..., : H * 64] *= 0.125
-    qkv = qkv.bfloat16().cuda()
+    dtype, tol = (torch.float32, 2e-5) if backend == 2 else (torch.bfloat16, 2e-2)
+    qkv = qkv.to(dtype).cuda()
     lens_t = lens.to(device="cuda", dtype=torch.int64)
-    out = torch.full((B, T, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out = torch.full((B, T, H * 64), float("nan"), device="cuda", dtype=dtype)
     _lib.check(lib.swc_test_attention(backend, _p(qkv), _p(out), _p(lens_t), B, T, H, _stream()), "attention")
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
@@ -144,4 +147,4 @@ def test_attention_many_items_mixed_lengths(backend):
     for b in (0, 1, 3, 4, 6, 7, 20, 39):                                      # reference on a subset (memory)
         ref = _attn_ref(qkv[b:b + 1], lens_t[b:b + 1], H)
         diff = ((out[b:b + 1].double() - ref) * ok[b:b + 1, :, None]).abs().max().item()
-        assert diff < 2e-2, (b, int(lens[b]), diff)
+        assert diff < tol, (b, int(lens[b]), diff)

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Micro-benchmark of the bf16 attention kernels at the codec's shape (B x 1500 tokens x 12 heads x 64)."""
+"""Micro-benchmark of the attention kernels at the codec's shape (B x 1500 tokens x 12 heads x 64).
+backends: 3 = bf16 tcgen05, 2 = three-product (bf16x3) tcgen05 behind an fp32 interface (the timing of that entry includes
+the plane split / merge passes and two cudaMalloc: use the whole-model bench for its real cost), 1 / 0 = SIMT bf16 / fp32."""
 import ctypes as C
 import json
 import os
@@ -13,18 +15,20 @@ from simwhisper_codec_b200 import _lib  # noqa: E402
 
 def main():
     lib = _lib.load()
-    backends = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["2", "3"])]
+    backends = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["3"])]
     B, T, H = int(os.environ.get("AB_B", 64)), int(os.environ.get("AB_T", 1500)), 12
     reps = int(os.environ.get("AB_REPS", 5))
     g = torch.Generator(device="cuda").manual_seed(1)
-    qkv = torch.randn(B, T, 3 * H * 64, device="cuda", generator=g) * 0.7
-    qkv[..., : H * 64] *= 0.125          # the packed q_proj carries the 1/sqrt(head_dim) scale
-    qkv = qkv.bfloat16()
+    base = torch.randn(B, T, 3 * H * 64, device="cuda", generator=g) * 0.7
+    base[..., : H * 64] *= 0.125          # the packed q_proj carries the 1/sqrt(head_dim) scale
     lens = torch.full((B,), T, device="cuda", dtype=torch.int64)
-    out = torch.empty(B, T, H * 64, device="cuda", dtype=torch.bfloat16)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     ref = None
     for be in backends:
+        dt = torch.float32 if be in (0, 2) else torch.bfloat16
+        qkv = base.to(dt)
+        out = torch.empty(B, T, H * 64, device="cuda", dtype=dt)
+
         def run():
             _lib.check(lib.swc_test_attention(be, C.c_void_p(qkv.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(lens.data_ptr()),
                                               B, T, H, st), "attention")
