@@ -93,27 +93,71 @@ class ClockSampler(threading.Thread):
                 "power_w_max": top or None}
 
 
-def cpu_reference_run(steps, warmup, windows_per_step=1):
-    """Reference algorithm (oracle port, fp32) on all host threads; one step = `windows_per_step` windows."""
-    from oracle import port
+def find_reference_tree():
+    """The real reference, if a copy is reachable on this box: $SIMWHISPER_REF, baseline/_ref, /root/reference."""
+    for cand in (os.environ.get("SIMWHISPER_REF"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if cand and os.path.exists(os.path.join(cand, "audiocodec", "model.py")):
+            return cand
+    return None
+
+
+def cpu_reference_run(steps, warmup, items=4):
+    """The reference algorithm in fp32 on all host threads.  One step = the same call sequence as the GPU arm's step
+    (single-pass inference_tokenize -> inference_detokenize) on `items` x 30 s windows (B = 4; 256
+    windows would take half an hour of CPU time per step).  The real reference is used when a copy of its tree is reachable
+    (kind "reference"), else the pinned oracle port (kind "port").  Returns the MEDIAN step."""
     from simwhisper_codec_b200.weights import random_state_dict
     torch.set_num_threads(os.cpu_count())
-    sd = random_state_dict(gen_params(), seed=0, exercise=True)
-    x = synthetic_batch(windows_per_step)[:, None, :]
-    lens = torch.full((windows_per_step,), WIN, dtype=torch.long)
+    gp = gen_params()
+    sd = random_state_dict(gp, seed=0, exercise=True)
+    x = synthetic_batch(items)[:, None, :]
+    lens = torch.full((items,), WIN, dtype=torch.long)
+    ref_tree = find_reference_tree()
+    kind = "port"
+    if ref_tree is not None:
+        try:
+            import importlib
+            import warnings
+            warnings.filterwarnings("ignore")
+            sys.dont_write_bytecode = True
+            sys.path.insert(0, ref_tree)
+            for name in [m for m in sys.modules if m == "audiocodec" or m.startswith("audiocodec.") or m == "utils" or m.startswith("utils.")]:
+                del sys.modules[name]
+            RefCodec = importlib.import_module("audiocodec.model").AudioCodec
+            ref = RefCodec(yaml.safe_load(open(os.path.join(ref_tree, "config", "SimWhisperCodec.yaml")))["generator_params"]).eval()
+            ref.load_state_dict(sd, strict=True)
+            kind = "reference"
+        except Exception as e:      # an unusable copy: fall back to the port, say so
+            print(f"[bench] reference tree at {ref_tree} not usable ({str(e)[:120]}); timing the oracle port", file=sys.stderr)
+            sys.path.remove(ref_tree)
+    if kind == "reference":
+        def step():
+            with torch.inference_mode():
+                r = ref.inference_tokenize(x, lens)
+                ref.inference_detokenize(r["codes"], r["codes_lengths"])
+    else:
+        from oracle import port
 
-    def step():
-        with torch.inference_mode():
-            r = port.tokenize(sd, x, lens)
-            port.detokenize(sd, r["codes"], r["codes_lengths"])
+        def step():
+            with torch.inference_mode():
+                r = port.tokenize(sd, x, lens)
+                port.detokenize(sd, r["codes"], r["codes_lengths"])
 
     for _ in range(warmup):
         step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    times = []
+    for _ in range(max(steps, 1)):
+        t0 = time.perf_counter()
         step()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return windows_per_step * 30.0 / dt, dt
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": items * 30.0 / med, "seconds_per_step": med, "kind": kind, "items": items, "steps": len(times),
+            "spread": (times[-1] - times[0]) / med if len(times) > 1 else None,
+            "sample": f"{items} x 30 s windows per step (single-pass inference_tokenize -> inference_detokenize, fp32), median of "
+                      f"{len(times)} step(s) after {warmup} warm-up, "
+                      + ("the reference's own AudioCodec on CPU" if kind == "reference" else "oracle/port.py (the reference's ATen ops restated)")
+                      + f", {os.cpu_count()} host threads"}
 
 
 def main():
@@ -132,6 +176,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-leg", action="store_true",
                     help="skip the extra measurement of the parity-grade precision (bf16x3) at N = 1")
+    ap.add_argument("--no-check", action="store_true", help="skip the output check of the timed configuration against bf16x3")
+    ap.add_argument("--sharded-api", default="auto", choices=["auto", "on", "off"],
+                    help="also run ShardedCodec.encode+decode on BASELINE configs[3] / a scaled configs[4] (auto: when N > 1)")
     args = ap.parse_args()
 
     # stdout carries exactly one JSON line: anything libraries print meanwhile (NCCL's version banner, ...) goes to stderr
@@ -156,15 +203,27 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        warm = min(args.warmup, 1)
-        v, dt = cpu_reference_run(args.steps, warm)
+        # a bounded sample of the same workload: 4 of the 256 windows per step, fp32, all host threads; the run is sized to end
+        # within a few minutes whatever --steps says (a step is ~5 s of CPU time on 16 cores)
+        items = 4
+        steps = max(3, min(args.steps, 12))
+        warm = max(1, min(args.warmup, 2))
+        r = cpu_reference_run(steps, warm, items)
+        ref_config = dict(config)
+        ref_config["workload"] = (f"BASELINE.json configs[2] on the host CPU: the same single-pass inference_tokenize->inference_detokenize, "
+                                  f"{items} x 30 s windows per step (a bounded sample of the 256-window batch), fp32, random-init "
+                                  "SimWhisperCodec.yaml weights")
+        ref_config["windows_per_step"] = items
+        ref_config["precision"] = "fp32"
+        del ref_config["windows_per_gpu"]
         emit({
-            "impl": "reference", "metric": "audio-sec/sec encode+decode (16 kHz)", "value": v, "unit": "audio-s/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": "1 x 30 s window per step (tokenize+detokenize), oracle/port.py on all host threads"},
-            "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "impl": "reference", "metric": "audio-sec/sec encode+decode (16 kHz)", "value": r["value"], "unit": "audio-s/s",
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": warm, "ms_per_step": r["seconds_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": ref_config,
+            "cpu_baseline": {"value": r["value"], "unit": "audio-s/s", "cores": os.cpu_count(), "kind": r["kind"],
+                             "sample": r["sample"], "spread": r["spread"]},
+            "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0})
         return
 
@@ -178,9 +237,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # rank 0 must print exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off stdout
-        if not os.environ.get("SWC_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # (NCCL's banner / NCCL_DEBUG output cannot reach the JSON line: fd 1 points at stderr until emit())
         dist.init_process_group("nccl", device_id=dev)
 
     gp = gen_params()
@@ -285,10 +342,6 @@ def main():
     ms_e2e = timed(step_e2e, args.steps)
     e2e = world * B * 30.0 / (ms_e2e * 1e-3)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -308,40 +361,140 @@ def main():
                 "avg_launch_ms": gemm_ms / max(cls_n["gemm_tcgen05"], 1),
                 "class_ms_per_step": cls_ms, "class_share": {k: v / tot_cls for k, v in cls_ms.items()},
                 "class_launches": cls_n}
-    # the same single pass in the parity-grade precision (fp32 activations, three-product split-bf16 contractions: index flips
-    # < 0.1 %, decode SNR > 90 dB vs the reference): informational, N = 1 only, 64 windows resident in HBM
+    def snr_db(ref, est):
+        ref, est = ref.double().reshape(-1), est.double().reshape(-1)
+        return float(10 * torch.log10((ref ** 2).sum() / ((ref - est) ** 2).sum().clamp_min(1e-300)))
+
+    # ---- the timed configuration's own output, checked on this device against the parity-grade mode (bf16x3, which the
+    #      GPU tests hold to the fp32 bars against the reference): 8 of the 256 windows, codes and waveform
+    check = None
+    if not args.no_check and args.precision == "bf16":
+        pick = sorted({int(round(i * (B - 1) / 7)) for i in range(8)})
+        r_all = model.inference_tokenize(x_dev, lens)                       # the timed step's call, outputs kept this time
+        y_all = model.inference_detokenize(r_all["codes"], r_all["codes_lengths"])["y"]
+        codes16 = r_all["codes"][:, pick].clone()
+        finite = bool(torch.isfinite(y_all).all())
+        rms = float(y_all[pick].float().pow(2).mean().sqrt())
+        del r_all, y_all
+        mx = AudioCodec(gp, precision="bf16x3", max_batch=len(pick))
+        mx.load_state_dict(random_state_dict(gp, seed=0, exercise=True))
+        xs = host_x[pick].to(dev)[:, None, :]
+        r3 = mx.inference_tokenize(xs, lens[pick])
+        flip = float((codes16 != r3["codes"]).float().mean())
+        y3 = mx.inference_detokenize(r3["codes"], r3["codes_lengths"])["y"]
+        y16 = model.inference_detokenize(r3["codes"], r3["codes_lengths"])["y"]   # identical codes through the timed mode
+        snr = snr_db(y3, y16)
+        check = {"windows": pick, "flip_rate": flip, "snr_db": snr, "finite": finite, "rms": rms,
+                 "bounds": {"flip_rate_max": 0.05, "snr_db_min": 38.0},
+                 "ok": bool(finite and flip <= 0.05 and snr >= 38.0),
+                 "what": "codes of the timed bf16 step vs bf16x3 on the same inputs; bf16 vs bf16x3 waveform on identical codes"}
+        del mx, xs, r3, y3, y16
+        torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[3] / [4] through the sharded public API (windows dealt to the ranks, codes all-gathered, waveforms
+    #      gathered to rank 0): valid audio-seconds per second, host planning and copies included
+    sharded_api = None
+    if args.sharded_api == "on" or (args.sharded_api == "auto" and world > 1):
+        from simwhisper_codec_b200.parallel import ShardedCodec
+        if world == 1 and not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29577")
+            dist.init_process_group("gloo", rank=0, world_size=1)
+        sc = ShardedCodec(model)
+
+        def run_api(lens_s, reps=2):
+            g = torch.Generator().manual_seed(7)
+            wavs = [(0.1 * torch.randn(n, generator=g)).clamp_(-1, 1) for n in lens_s]
+            sub = wavs[:8]                                   # correctness on a subset: every rank takes part
+            c_sh = sc.encode(sub, device=dev)["codes_list"]
+            w_sh = sc.decode(c_sh, device=dev)["syn_wav_list"]
+            ok = None
+            if rank == 0:
+                c_1 = model.encode(sub, device=dev)["codes_list"]
+                w_1 = model.decode(c_1, device=dev)["syn_wav_list"]
+                ok = all(torch.equal(a, b) for a, b in zip(c_sh, c_1)) and all(torch.equal(a, b) for a, b in zip(w_sh, w_1))
+            best = None
+            for _ in range(reps + 1):                        # the first pass warms the workspaces
+                barrier()
+                t0 = time.perf_counter()
+                codes = sc.encode(wavs, device=dev)["codes_list"]
+                sc.decode(codes, device=dev)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                best = float(t[0]) if best is None else min(best, float(t[0]))
+            secs = sum(lens_s) / SR
+            return {"value": secs / best, "unit": "valid audio-s/s", "items": len(lens_s), "audio_seconds": secs,
+                    "windows": sum((n + 319999) // 320000 for n in lens_s), "wall_s": best, "equals_single_gpu": ok}
+
+        gl = torch.Generator().manual_seed(123)
+        lens3 = [int(SR * (2 + 28 * float(torch.rand((), generator=gl)))) for _ in range(256)]
+        long_items = 4 * world
+        sharded_api = {"configs[3]": run_api(lens3), "configs[4]": run_api([SR * 600] * long_items),
+                       "note": "ShardedCodec.encode + decode (default overlap 10 s), wall clock incl. host planning, H2D, NCCL gather of "
+                               "codes (all ranks) and waveforms (rank 0); configs[3] = 256 items of 2-30 s (strong scaling: fixed "
+                               f"job), configs[4] scaled to {long_items} items of 10 min (4 per GPU, 30 windows each); best of 2"}
+
+    # ---- the same single pass in the parity-grade precision (fp32 activations, three-product split-bf16 contractions and
+    #      attention on tcgen05: index flips < 0.1 %, decode SNR > 90 dB vs the reference) at the FULL batch, with its own
+    #      class timings and roofline: N = 1 only
     parity_mode = None
     if world == 1 and not args.no_parity_leg and args.precision == "bf16":
         try:
             del x_dev
             model._native = None
             torch.cuda.empty_cache()
-            pb = min(64, B)
-            mx = AudioCodec(gp, precision="bf16x3", max_batch=pb)
+            mx = AudioCodec(gp, precision="bf16x3", max_batch=args.max_batch)
             mx.load_state_dict(random_state_dict(gp, seed=0, exercise=True))
-            xx = host_x[:pb].to(dev)[:, None, :]
-            ll = lens[:pb]
+            xx = host_x.to(dev)[:, None, :]
 
             def step_x3():
-                r = mx.inference_tokenize(xx, ll)
+                r = mx.inference_tokenize(xx, lens)
                 return mx.inference_detokenize(r["codes"], r["codes_lengths"])
 
             for _ in range(2):
                 step_x3()
-            ms_x3 = timed(step_x3, 2)
-            parity_mode = {"precision": "bf16x3", "value": pb * 30.0 / (ms_x3 * 1e-3), "unit": "audio-s/s", "windows": pb,
-                           "ms_per_step": ms_x3,
-                           "note": "fp32 activations, dense contractions and attention as three bf16 products with fp32 "
-                                   "accumulation; meets the fp32 parity bars (tests/test_gpu_parity.py::test_bf16x3_mode_meets_the_fp32_bars)"}
+            sampler3 = ClockSampler(local)
+            sampler3.start()
+            time.sleep(0.2)
+            ms_x3 = timed(step_x3, max(2, min(args.steps, 3)))
+            clocks3 = sampler3.stop()
+            step_x3()
+            lib.swc_profile(1)
+            step_x3()
+            torch.cuda.synchronize()
+            lib.swc_profile_read(ms_cls, n_cls, 8)
+            lib.swc_profile(0)
+            cls3 = {k: float(ms_cls[i]) for i, k in enumerate(_lib.KCLASS)}
+            g3 = cls3["gemm_tcgen05"]
+            # three bf16 products per contraction: the tensor pipe does 3x the algorithmic FLOPs
+            alg = (GF_TC_GEMM * B / 1e3) / (g3 * 1e-3) if g3 > 0 else 0.0
+            parity_mode = {"precision": "bf16x3", "value": B * 30.0 / (ms_x3 * 1e-3), "unit": "audio-s/s", "windows": B,
+                           "ms_per_step": ms_x3, "clocks": clocks3, "class_ms_per_step": cls3,
+                           "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel, three-product (hi|lo) operands",
+                                        "achieved_algorithmic": alg, "achieved": 3 * alg, "peak": peak_tf, "unit": "TFLOP/s",
+                                        "frac": 3 * alg / peak_tf if peak_tf else None,
+                                        "note": "achieved = bf16 tensor-pipe work (3 products per contraction) / GEMM-class time; "
+                                                "achieved_algorithmic counts every contraction once"},
+                           "attention_tflops_algorithmic": (GF_ATTN * B / 1e3) / (cls3["attention"] * 1e-3) if cls3["attention"] > 0 else None,
+                           "note": "fp32 activations, dense contractions and attention as three bf16 products with fp32 accumulation on "
+                                   "tcgen05; meets the fp32 parity bars (tests/test_gpu_parity.py::test_bf16x3_mode_meets_the_fp32_bars, "
+                                   "test_config1_all_64_windows)"}
             del mx, xx
             torch.cuda.empty_cache()
         except Exception as e:      # informational leg: never fail the bench line
             parity_mode = {"precision": "bf16x3", "error": str(e)[:200]}
+    if rank != 0:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+        return
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
-        v, dt = cpu_reference_run(1, 1)
-        cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
-                        "sample": "1 x 30 s window (tokenize+detokenize, fp32) after 1 warm-up, oracle/port.py, all host threads"}
+        r = cpu_reference_run(3, 1, 4)
+        cpu_baseline = {"value": r["value"], "unit": "audio-s/s", "cores": os.cpu_count(), "kind": r["kind"],
+                        "sample": r["sample"], "spread": r["spread"]}
     out = {
         "metric": "audio-sec/sec encode+decode (16 kHz)", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -352,11 +505,13 @@ def main():
                 "api": f"AudioCodec.inference_tokenize -> inference_detokenize per {e2e_chunk}-window chunk from pinned host buffers; "
                        "H2D / compute / D2H of consecutive chunks and steps overlap on three streams"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "parity_mode": parity_mode,
+        "check": check, "parity_mode": parity_mode, "sharded_api": sharded_api,
     }
     emit(out)
-    if world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
+    if check is not None and not check["ok"]:
+        raise SystemExit(f"bench.py: the timed configuration's output failed its check: {check}")
 
 
 if __name__ == "__main__":

@@ -123,16 +123,36 @@ def test_bf16_mode_reported_separately(model16, model32):
     codes = r["codes"][:, 0, :125].cpu()
     flips = (codes != torch.from_numpy(g["codes"])).float().mean().item()
     print(f"bf16 index flip rate vs fp32 reference: {flips:.4f}")
-    assert flips < 0.25
+    assert flips < 0.06            # observed 0.029-0.039 (the reference's own pure-bf16 run flips 4.1 %)
     wav = model16.decode([torch.from_numpy(g["codes"])])["syn_wav_list"][0]
     s = snr_db(torch.from_numpy(g["wav"]), wav.cpu())
     print(f"bf16 decode SNR vs fp32 reference (same codes): {s:.1f} dB")
-    assert s > 25.0
+    assert s > 38.0                # observed 42 dB (the reference under bf16 autocast: 37.9 dB)
     # tcgen05 path vs the SIMT kernels on the same bf16 operands: same arithmetic up to accumulation order
     g2 = load_golden("forward_small_ex.npz")
     a = model16({"mel_features": _cuda(g2["mel"]), "mel_lens": _cuda(g2["mel_lens"])})["reconstructed_audio"]
     assert torch.isfinite(a).all()
-    assert snr_db(torch.from_numpy(g2["audio"]), a.cpu()) > 20.0
+    s2 = snr_db(torch.from_numpy(g2["audio"]), a.cpu())
+    print(f"bf16 end-to-end forward SNR vs fp32 reference (own codes, flips included): {s2:.1f} dB")
+    assert s2 > 20.0               # end to end through the quantizer: a flipped index changes the waveform, the bound is loose on purpose
+
+
+def test_bf16_per_stage_vs_reference_goldens(model16):
+    """bf16 mode stage by stage, each fed the reference's own input (no error accumulation across stages, no index flips):
+    a wrong GELU / softmax approximation or a dropped bias shows up here even though the end-to-end bound is loose."""
+    g = load_golden("forward_small_ex.npz")
+    mel, lens = _cuda(g["mel"]), _cuda(g["mel_lens"])
+    enc, el = model16.acoustic_encoder(mel, lens)
+    lat, ll = model16.downsample(_cuda(g["enc"]), el)
+    up, ul = model16.upsample(_cuda(g["zq"]), ll)
+    dec, dl = model16.acoustic_decoder(_cuda(g["up"]), ul)
+    y, yl = model16.vocos(_cuda(g["dec"]), dl)
+    got = {"enc": snr_db(torch.from_numpy(g["enc"]), enc.cpu()), "latent": snr_db(torch.from_numpy(g["latent"]), lat.cpu()),
+           "up": snr_db(torch.from_numpy(g["up"]), up.cpu()), "dec": snr_db(torch.from_numpy(g["dec"]), dec.cpu()),
+           "audio": snr_db(torch.from_numpy(g["audio"]), y.cpu())}
+    print("bf16 per-stage SNR vs reference (dB):", {k: round(v, 1) for k, v in got.items()})
+    for k, v in got.items():
+        assert v > 36.0, (k, v)
 
 
 def test_full_window_properties_fp32(model32):
@@ -167,26 +187,30 @@ def test_full_window_vs_oracle_fp32(model32, sd_ex):
     assert snr_db(ref_wav["y"], out["y"].cpu()) >= 40.0
 
 
-def test_config1_batch64_fp32_indices(model32, sd_ex):
-    """BASELINE configs[1]: encoder + quantizer only, batch 64 x 30 s, fp32 mode.  Two of the 64 windows are checked
-    against the CPU oracle (bit-exact indices up to near-tie flips < 0.1 %), the rest through batch independence (a
-    window's codes do not depend on its neighbours) and the code alphabet (8 groups x 2016 levels)."""
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
+def test_config1_all_64_windows(mode, model32, model_x3):
+    """BASELINE configs[1]: encoder + quantizer only, batch 64 x 30 s.  ALL 64 windows against the codes the real reference
+    produced for the same inputs (tests/golden/enc64_ex.npz, made by make_goldens_r2.py): bit-exact indices up to near-tie
+    flips < 0.1 %, in the CUDA-core fp32 mode and in the tensor-core parity mode."""
+    m = model32 if mode == "fp32" else model_x3
+    g = load_golden("enc64_ex.npz")
     B = 64
-    x = torch.stack([synthetic_wave(7000 + i, 480000) for i in range(B)])[:, None, :]
+    x = torch.stack([synthetic_wave(1000 + i, 480000) for i in range(B)])[:, None, :]
     lens = torch.full((B,), 480000)
-    r = model32.inference_tokenize(x.cuda(), lens.cuda())
+    r = m.inference_tokenize(x.cuda(), lens.cuda())
     codes = r["codes"].cpu()
     assert codes.shape == (8, B, 375) and codes.dtype == torch.int32
-    assert r["codes_lengths"].tolist() == [375] * B
+    assert r["codes_lengths"].tolist() == g["codes_lengths"].tolist() == [375] * B
     assert int(codes.min()) >= 0 and int(codes.max()) < 2016
-    with torch.inference_mode():
-        ref = port.tokenize(sd_ex, x[[0, 63]], lens[[0, 63]])
-    flips = (codes[:, [0, 63]] != ref["codes"]).float().mean().item()
+    ref = torch.from_numpy(g["codes"].astype("int32"))
+    per_window = (codes != ref).float().mean(dim=(0, 2))
+    flips = float((codes != ref).float().mean())
+    print(f"{mode}: index flips vs the reference over 64 x 30 s windows: {flips:.6f} (worst window {float(per_window.max()):.5f})")
     assert flips < 1e-3, flips
-    for i in (17, 40):
-        solo = model32.inference_tokenize(x[i:i + 1].cuda(), lens[i:i + 1].cuda())
+    assert float(per_window.max()) < 4e-3, per_window.max()           # no single window carries the flips (3000 indices each)
+    for i in (17, 40):                                                 # a window's codes do not depend on its neighbours
+        solo = m.inference_tokenize(x[i:i + 1].cuda(), lens[i:i + 1].cuda())
         assert torch.equal(solo["codes"][:, 0].cpu(), codes[:, i])
-    # distinct inputs give distinct code streams (no aliasing of batch slots)
     assert len({codes[:, i].numpy().tobytes() for i in range(B)}) == B
 
 
@@ -215,13 +239,13 @@ def test_bf16_full_window_properties(model16, model32, gen_params, sd_ex):
     valid = torch.arange(375, device="cuda")[None, None, :] < r["codes_lengths"][None, :, None]
     flips = ((r["codes"] != r32["codes"]) & valid).sum().item() / (8 * int(r["codes_lengths"].sum()))
     print(f"bf16 vs fp32 (same device) index flip rate on 30 s windows: {flips:.4f}")
-    assert flips < 0.25
+    assert flips < 0.06
     y16 = model16.inference_detokenize(r32["codes"], r32["codes_lengths"])
     y32 = model32.inference_detokenize(r32["codes"], r32["codes_lengths"])
     assert y16["output_length"].tolist() == y32["output_length"].tolist() == [480000, 480000, 240640, 99840, 480000]
     s = snr_db(y32["y"][0, 0].cpu(), y16["y"][0, 0].cpu())
     print(f"bf16 vs fp32 decode SNR (same codes, 30 s): {s:.1f} dB")
-    assert s > 30.0
+    assert s > 38.0
     y2 = small.inference_detokenize(r32["codes"], r32["codes_lengths"])
     assert torch.equal(y2["y"], y16["y"])
 
@@ -343,3 +367,63 @@ def test_api_edge_cases_fp32(model32, sd_ex):
     assert [tuple(c.shape) for c in e] == [(8, 0), (8, 0)]
     d = model32.decode([torch.zeros(8, 0, dtype=torch.long), torch.zeros(8, 0, dtype=torch.long)])["syn_wav_list"]
     assert [len(w) for w in d] == [0, 0]
+
+
+def test_encoder_hidden_states_fp32(model32):
+    """OmniAudioEncoder.forward(output_hidden_states=True) (reference modules.py:344-371): the masked input of each of the
+    12 layers and the final LayerNorm output, against the reference's own tensors."""
+    g = load_golden("hidden_small_ex.npz")
+    f = load_golden("forward_small_ex.npz")
+    out, ol, hs = model32.acoustic_encoder(_cuda(f["mel"]), _cuda(f["mel_lens"]), output_hidden_states=True)
+    assert len(hs) == 13 and ol.tolist() == g["out_len"].tolist()
+    assert (out.cpu()[:, ::8] - torch.from_numpy(g["out"])).abs().max().item() < 5e-5
+    for i, h in enumerate(hs):
+        assert tuple(h.shape) == (2, 768, 100)
+        assert (h.cpu()[:, ::8] - torch.from_numpy(g["hidden"][i])).abs().max().item() < 1e-4, i
+    assert float(hs[5][1, :, 68:].abs().max()) == 0.0
+    plain = model32.acoustic_encoder(_cuda(f["mel"]), _cuda(f["mel_lens"]))
+    assert torch.equal(plain[0], out)
+
+
+def test_whisper_like_outlier_channels(gen_params):
+    """Whisper-like statistics: four residual-stream channels at 30-80x the magnitude of the rest (weights.random_state_dict
+    (outlier_gain=50); trained Whisper encoders have such channels, random init has none).  The tensor-core modes must keep
+    their accuracy there: bf16x3 stays parity-grade, bf16 stays finite and close to its benign-statistics figures, so the
+    reference's half-precision inf/nan clamp (modules.py:228-231) has nothing to catch: the residual stream is fp32 in every
+    mode and the largest GEMM operand (a LayerNorm output, |x| < 30) is far inside the bf16 range."""
+    from simwhisper_codec_b200.weights import random_state_dict
+    g = load_golden("outlier_ex.npz")
+    sd = random_state_dict(gen_params, seed=0, exercise=True, outlier_gain=50.0)
+    mel, lens = _cuda(g["mel"]), _cuda(g["mel_lens"])
+    ref_codes = torch.from_numpy(g["codes"])
+    res = {}
+    for mode in ("bf16x3", "bf16"):
+        m = AudioCodec(gen_params, precision=mode)
+        m.load_state_dict(sd)
+        enc, el = m.acoustic_encoder(mel, lens)
+        lat, ll = m.downsample(enc, el)
+        _, codes = m.quantizer(lat, ll)
+        up, ul = m.upsample(m.quantizer.decode(_cuda(g["codes"]), ll), ll)     # decode path on the reference's own codes
+        dec, _ = m.acoustic_decoder(up, ul)
+        assert torch.isfinite(enc).all() and torch.isfinite(dec).all()
+        res[mode] = {"enc_snr": snr_db(torch.from_numpy(g["enc"]), enc.cpu()),
+                     "flips": float((codes.cpu() != ref_codes).float().mean()),
+                     "dec_snr": snr_db(torch.from_numpy(g["dec"]), dec.cpu())}
+    print("outlier-channel stress:", {k: {a: round(b, 4) for a, b in v.items()} for k, v in res.items()})
+    assert res["bf16x3"]["flips"] < 2e-3 and res["bf16x3"]["enc_snr"] > 80 and res["bf16x3"]["dec_snr"] > 60
+    assert res["bf16"]["flips"] < 0.10 and res["bf16"]["enc_snr"] > 30 and res["bf16"]["dec_snr"] > 30
+
+
+def test_overlap_other_than_default_fp32(model32, sd_ex):
+    """overlap_seconds 5 (hop not a multiple of 1280 samples: the reference's code axis drifts, trailing codes are zero)
+    and 0, through encode()/decode(), against the oracle's restatement of the reference's chunk loops."""
+    lens = [1200000, 500000, 48123]
+    wavs = [synthetic_wave(9500 + i, n) for i, n in enumerate(lens)]
+    for ov in (5, 0):
+        with torch.inference_mode():
+            ref_codes = port.encode(sd_ex, wavs, overlap_seconds=ov)
+        codes = model32.encode(wavs, overlap_seconds=ov)["codes_list"]
+        assert [tuple(c.shape) for c in codes] == [tuple(c.shape) for c in ref_codes]
+        total = sum(c.numel() for c in codes)
+        flips = sum((c.cpu().long() != r.long()).sum().item() for c, r in zip(codes, ref_codes))
+        assert flips / total < 1e-3, (ov, flips, total)
