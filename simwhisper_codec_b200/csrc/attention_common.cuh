@@ -15,6 +15,14 @@ constexpr int QT = 128, KT = 128, HD = 64;
 constexpr int kTileBytes = 128 * 64 * 2;                 // 16 KB: one Q, K or V tile (128 rows x 64 bf16)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;                // log2 units
+// Thread layout of both kernels: warpgroup 0 = warp 0 TMA producer, warps 1 / 2 MMA issuers of query tile 0 / 1, warp 3 idle;
+// warpgroups 1-4 = the 16 softmax warps.  The kernels are launched at 96 registers per thread (640 x 96 = 60 K of the 64 K
+// register file); warpgroup 0 shrinks to kRegsIssue and hands its registers to the softmax warpgroups, which grow to
+// kRegsSoftmax (128 x 48 + 512 x 104 = 58 K): the softmax threads hold 64 scores, 32 packed probabilities and the loop state.
+constexpr int kThreads = 128 + 512;
+constexpr int kRegsIssue = 48, kRegsSoftmax = 104;
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // n / d by one multiply-high (exact while n * d < 2^32): the per-item decode runs on every role's critical path
 struct FastDiv {
@@ -29,7 +37,6 @@ struct AttnParams {
   FastDiv by_qp, by_h, by_qph;
   long long* trace;        // optional per-phase clock64 stamps of CTA 0 (tools/attn_trace.py); null in normal runs
   int fine;                // trace: four more stamps per key block (perturbs the kernel)
-  int skew;                // cycles the softmax warps of query tile 1 wait at kernel start (phase offset between the tiles)
 };
 // RAGGED: rows are packed (item b = rows [off[b], off[b] + len[b])), lengths come with the launch (no global load per
 // item), and rows >= len[b] do not exist: nothing is written for them.
@@ -101,18 +108,9 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
-template <int N>
-__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
-  static_assert(N == 32 || N == 64, "tmem_ld_n");
-#pragma unroll
-  for (int c = 0; c < N / 32; ++c) tmem_ld32(taddr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
-}
-template <int N>
-__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]) {
-  static_assert(N == 32 || N == 64, "tmem_st_n");
-#pragma unroll
-  for (int c = 0; c < N / 32; ++c) tmem_st32(taddr + c * 32, *reinterpret_cast<const uint32_t(*)[32]>(&r[c * 32]));
-}
+// (no pointer casts into sub-arrays: they force the register array into local memory)
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st32(taddr, r); }
 
 }  // namespace attn
 }  // namespace swc

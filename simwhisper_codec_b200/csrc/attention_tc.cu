@@ -43,7 +43,7 @@ constexpr int kSmemBytes = kOutOff + 2 * kTileBytes + 1024;
 constexpr uint32_t kColS = 0, kColP = 256, kColO = 384;
 
 template <int SPLIT, typename TAB>
-__global__ void __launch_bounds__(96 + 256 * SPLIT, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, const __grid_constant__ TAB tab) {
   constexpr bool kRagged = std::is_same<TAB, RaggedTable>::value;
   extern __shared__ uint8_t smem_raw[];
@@ -78,6 +78,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
   const int D3 = 3 * p.H * HD;
+
+  if (warp < 4) setmaxnreg_dec<kRegsIssue>();
+  else setmaxnreg_inc<kRegsSoftmax>();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -200,13 +203,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         advance(cp);
       }
     }
-  } else {
+  } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax warps
     // SPLIT threads share one query row: thread `part` owns key columns [part*NC, part*NC + NC) of S / P and output
     // dims [part*ND, part*ND + ND) of O.  With SPLIT = 2 there are 16 softmax warps (4 per scheduler instead of 2)
     // to hide the MUFU / TMEM latencies; the row maximum and the final row sum are combined through shared memory.
     constexpr int NC = KT / SPLIT, ND = HD / SPLIT;
-    const int sw = warp - 3;                          // softmax warp index
+    const int sw = warp - 4;                          // softmax warp index
     const int i = sw / (4 * SPLIT);                   // query tile
     const int part = (sw >> 2) % SPLIT;               // column part of the row
     const int lg = warp & 3;                          // TMEM lane group this warp may access
@@ -223,10 +226,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
     const int tslot = i;
     uint8_t* ostage = smem + kOutOff + i * kTileBytes;
     long long len_next = blockIdx.x < p.n_items ? item_len_raw(p, tab, blockIdx.x) : 0;
-    if (p.skew > 0 && i == 1) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < p.skew) {}
-    }
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const Item it = decode_item(p, tab, item, len_next);
       if (item + (int)gridDim.x < p.n_items) len_next = item_len_raw(p, tab, item + gridDim.x);   // in flight during this item
@@ -241,35 +240,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
       }
       float m_used = -INFINITY, l = 0.f;
       if (tracer) trace_stamp(p, tslot, tr);                 // A: item decoded
+      const uint32_t sa = lane_addr + kColS + i * 128 + part * NC;
       for (int j = 0; j < it.n_kt; ++j) {
         mbar_wait(&s_full[i], s_cnt & 1);
         if (tracer) trace_stamp(p, tslot, tr);               // B: S ready
         ++s_cnt;
         tc_fence_after();
-        uint32_t s[NC];
-        {
-          const uint32_t sa = lane_addr + kColS + i * 128 + part * NC;
-#pragma unroll
-          for (int c = 0; c < NC / 32; ++c) tmem_ld32(sa + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
-          tmem_ld_wait();
-        }
+        uint32_t s0[32], s1[32];
+        tmem_ld32(sa, s0);
+        tmem_ld32(sa + 32, s1);
+        tmem_ld_wait();
         if (tracer && p.fine) trace_stamp(p, tslot, tr);               // B1: S in registers
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[i]);
+        // a barrier poll costs ~200 cycles of latency even when its phase is long complete: poll now, consume behind the exponentials
+        const bool pv_early = j > 0 && mbar_test(&o_done[i], o_cnt & 1);
         const int valid = it.len - j * KT - part * NC;      // valid keys among this thread's columns (may be <= 0)
         if (valid < NC) {
 #pragma unroll
-          for (int c = 0; c < NC; ++c) if (c >= valid) s[c] = 0xff800000u;   // -inf
+          for (int c = 0; c < 32; ++c) {
+            if (c >= valid) s0[c] = 0xff800000u;   // -inf
+            if (c + 32 >= valid) s1[c] = 0xff800000u;
+          }
         }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < NC; c += 4) {
-          mx[0] = fmaxf(mx[0], __uint_as_float(s[c])); mx[1] = fmaxf(mx[1], __uint_as_float(s[c + 1]));
-          mx[2] = fmaxf(mx[2], __uint_as_float(s[c + 2])); mx[3] = fmaxf(mx[3], __uint_as_float(s[c + 3]));
+        for (int c = 0; c < 32; c += 4) {
+          mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
+          mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(s0[c + 1]), __uint_as_float(s1[c + 1])));
+          mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(s0[c + 2]), __uint_as_float(s1[c + 2])));
+          mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(s0[c + 3]), __uint_as_float(s1[c + 3])));
         }
         float mxl = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kLog2e;
-        if constexpr (SPLIT > 1) {                    // combine the parts' maxima (double-buffered exchange slots)
+        {                                             // combine the parts' maxima (double-buffered exchange slots)
           const uint32_t slot = xch + (x_cnt & 1) * (SPLIT * QT * 4);
           ++x_cnt;
           sts_f32(slot + part * QT * 4, mxl);
@@ -280,40 +284,43 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         float scale = 1.0f;
         const bool grow = mxl > m_used + kRescaleThreshold;     // always true for j == 0 (m_used = -inf)
         if (grow) { scale = ex2(m_used - mxl); m_used = mxl; }   // j == 0: scale = 0, l = 0, O not yet written
-        uint32_t pk[NC / 2];
+        uint32_t pk0[16], pk1[16];
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
+        auto exp_half = [&](const uint32_t (&sh)[32], uint32_t (&pk)[16]) {
 #pragma unroll
-        for (int c = 0; c < NC; c += 4) {
-          const float p0 = ex2(fmaf(__uint_as_float(s[c]), kLog2e, -m_used));
-          const float p1 = ex2(fmaf(__uint_as_float(s[c + 1]), kLog2e, -m_used));
-          const float p2 = ex2(fmaf(__uint_as_float(s[c + 2]), kLog2e, -m_used));
-          const float p3 = ex2(fmaf(__uint_as_float(s[c + 3]), kLog2e, -m_used));
-          sum[0] += p0; sum[1] += p1; sum[2] += p2; sum[3] += p3;
-          pk[c >> 1] = pack2(p0, p1);
-          pk[(c >> 1) + 1] = pack2(p2, p3);
-        }
-        const float bsum = (sum[0] + sum[1]) + (sum[2] + sum[3]);
-        l = fmaf(l, scale, bsum);                       // this part's share of the row sum
+          for (int c = 0; c < 32; c += 4) {
+            const float p0 = ex2(fmaf(__uint_as_float(sh[c]), kLog2e, -m_used));
+            const float p1 = ex2(fmaf(__uint_as_float(sh[c + 1]), kLog2e, -m_used));
+            const float p2 = ex2(fmaf(__uint_as_float(sh[c + 2]), kLog2e, -m_used));
+            const float p3 = ex2(fmaf(__uint_as_float(sh[c + 3]), kLog2e, -m_used));
+            sum[0] += p0; sum[1] += p1; sum[2] += p2; sum[3] += p3;
+            pk[c >> 1] = pack2(p0, p1);
+            pk[(c >> 1) + 1] = pack2(p2, p3);
+          }
+        };
+        exp_half(s0, pk0);
+        exp_half(s1, pk1);
+        l = fmaf(l, scale, (sum[0] + sum[1]) + (sum[2] + sum[3]));   // this part's share of the row sum
         if (tracer && p.fine) trace_stamp(p, tslot, tr);               // B3: exponentials done
         if (j > 0) {
-          mbar_wait(&o_done[i], o_cnt & 1);             // P_i(j-1) V accumulated: P_i is free, O_i is stable
+          if (!pv_early) mbar_wait(&o_done[i], o_cnt & 1);   // P_i(j-1) V accumulated: P_i is free, O_i is stable
           ++o_cnt;
           tc_fence_after();
           if (__any_sync(0xffffffffu, grow)) {          // same rows, hence the same votes, in every part's warp
             const uint32_t oa = lane_addr + kColO + i * 64 + part * ND;
             uint32_t o[ND];
-            tmem_ld_n<ND>(oa, o);
+            tmem_ld_n(oa, o);
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < ND; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * scale);
-            tmem_st_n<ND>(oa, o);
+            tmem_st_n(oa, o);
           }
         }
         if (tracer && p.fine) trace_stamp(p, tslot, tr);               // B4: previous P V done (P slot free)
         {
           const uint32_t pa = lane_addr + kColP + i * 64 + part * (NC / 2);
-#pragma unroll
-          for (int c = 0; c < NC / 32; ++c) tmem_st16(pa + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]));
+          tmem_st16(pa, pk0);
+          tmem_st16(pa + 16, pk1);
           tmem_st_wait();
         }
         tc_fence_before();
@@ -327,7 +334,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
       ++o_cnt;
       tc_fence_after();
       uint32_t o[ND];
-      tmem_ld_n<ND>(lane_addr + kColO + i * 64 + part * ND, o);
+      tmem_ld_n(lane_addr + kColO + i * 64 + part * ND, o);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -406,9 +413,6 @@ int attention_tc_launch(const bf16* qkv, bf16* out, const long long* lens, long 
   p.by_qp.set((uint32_t)p.n_qp); p.by_h.set((uint32_t)H); p.by_qph.set((uint32_t)(p.n_qp * H));
   p.trace = g_attn_trace;
   p.fine = g_attn_trace_fine;
-  static const int skew = [] { const char* e = getenv("SWC_ATTN_SKEW"); return e ? atoi(e) : 0; }();
-  p.skew = skew;
-  static const int split = [] { const char* e = getenv("SWC_ATTN_SPLIT"); return (e && e[0] == '1') ? 1 : 2; }();
   const int grid = std::min(p.n_items, num_sms);
   ProfScope ps(KC_ATTN, s);
   auto go = [&](auto kern, int threads) -> int {
@@ -416,7 +420,7 @@ int attention_tc_launch(const bf16* qkv, bf16* out, const long long* lens, long 
     kern<<<grid, threads, kSmemBytes, s>>>(tm, p, tab);
     return 0;
   };
-  const int rc = split == 1 ? go(attention_tc_kernel<1, TAB>, 96 + 256) : go(attention_tc_kernel<2, TAB>, 96 + 512);
+  const int rc = go(attention_tc_kernel<2, TAB>, kThreads);      // two threads per query row (the one-thread-per-row form is gone)
   if (rc) return rc;
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;

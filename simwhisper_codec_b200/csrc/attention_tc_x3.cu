@@ -6,7 +6,7 @@
 //     O += P_h V_h + P_l V_h + P_h V_l                 (24 UMMA M128 N64 K16, A = P planes from TMEM, B = V MN-major)
 //
 // Same persistent, warp-specialised structure as attention_tc.cu (work item = (batch, head, two 128-query tiles); warp 0 TMA
-// producer, warps 1 / 2 MMA issuers of tile 0 / 1, warps 3-18 softmax, two threads per query row), with these differences:
+// producer, warps 1 / 2 MMA issuers of tile 0 / 1, warps 4-19 softmax, two threads per query row), with these differences:
 //   * the probabilities are split in registers, p = p_h + p_l, and written as two bf16 planes INTO THE COLUMNS OF S
 //     (S_i: 128 fp32 columns = P_h 64 + P_l 64 packed columns), so S_i(j+1) is issued behind P_i(j) V(j) by the same thread
 //     (the tensor pipe executes one thread's MMAs in order): no separate "S free" / "P V done" barriers inside an item, the
@@ -46,7 +46,7 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 }
 
 template <typename TAB>
-__global__ void __launch_bounds__(96 + 256 * SPLIT, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 attention_tc_x3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, const __grid_constant__ TAB tab) {
   constexpr bool kRagged = std::is_same<TAB, RaggedTable>::value;
   extern __shared__ uint8_t smem_raw[];
@@ -78,6 +78,9 @@ attention_tc_x3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
   const int D3 = 3 * p.H * HD;               // columns of one plane of a qkv row
+
+  if (warp < 4) setmaxnreg_dec<kRegsIssue>();
+  else setmaxnreg_inc<kRegsSoftmax>();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -180,10 +183,10 @@ attention_tc_x3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
         if (!last) issue_s(g + 1);                              // overwrites the P planes just consumed: same thread, in order
       }
     }
-  } else {
+  } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax warps
     constexpr int NC = KT / SPLIT, ND = HD / SPLIT;
-    const int sw = warp - 3;                          // softmax warp index
+    const int sw = warp - 4;                          // softmax warp index
     const int i = sw / (4 * SPLIT);                   // query tile
     const int part = (sw >> 2) % SPLIT;               // column part of the row
     const int lg = warp & 3;                          // TMEM lane group this warp may access
@@ -217,7 +220,7 @@ attention_tc_x3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
         ++s_cnt;
         tc_fence_after();
         uint32_t s[NC];
-        tmem_ld_n<NC>(s_addr + part * NC, s);
+        tmem_ld64(s_addr + part * NC, s);
         tmem_ld_wait();
         const int valid = it.len - j * KT - part * NC;      // valid keys among this thread's columns (may be <= 0)
         if (valid < NC) {
@@ -244,11 +247,11 @@ attention_tc_x3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
         if (grow) { scale = ex2(m_used - mxl); m_used = mxl; }   // j == 0: scale = 0, l = 0, O not yet written
         if (j > 0 && __any_sync(0xffffffffu, grow)) {            // same rows, hence the same votes, in both parts' warps
           uint32_t o[ND];
-          tmem_ld_n<ND>(o_addr, o);
+          tmem_ld_n(o_addr, o);
           tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < ND; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * scale);
-          tmem_st_n<ND>(o_addr, o);
+          tmem_st_n(o_addr, o);
         }
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
         // this thread's 64 keys = 32 packed columns per plane: P_h at [32 part, 32 part + 32), P_l 64 columns further
@@ -280,7 +283,7 @@ attention_tc_x3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPara
       ++o_cnt;
       tc_fence_after();
       uint32_t o[ND];
-      tmem_ld_n<ND>(o_addr, o);
+      tmem_ld_n(o_addr, o);
       tmem_ld_wait();
       {   // total row sum over the two parts
         const uint32_t slot = xch + (x_cnt & 1) * (SPLIT * QT * 4);
@@ -334,7 +337,7 @@ int attention_tc_x3_launch(const bf16* planes, bf16* out, const long long* lens,
   auto kern = attention_tc_x3_kernel<TAB>;
   SWC_TRY(ensure_dynamic_smem((const void*)kern, kSmemBytes));
   ProfScope ps(KC_ATTN, s);
-  kern<<<grid, 96 + 256 * SPLIT, kSmemBytes, s>>>(tm, p, tab);
+  kern<<<grid, kThreads, kSmemBytes, s>>>(tm, p, tab);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
