@@ -102,6 +102,28 @@ class NativeCodec:
         return _ptr(self._ws), C.c_size_t(self._ws.numel())
 
 
+class _GraphBucket:
+    """One captured call of the padded single-pass chain for a fixed (stage, batch, frames) bucket: static input / output /
+    workspace buffers, replayed with a single launch.  At one or a few windows a call is otherwise launch-bound on the host
+    (~880 launches per tokenize + detokenize at ~5 us each); the library allocates nothing, never synchronises and reads
+    nothing back, so the whole call captures as it is."""
+
+    def __init__(self, run, inputs, outputs, ws):
+        self.inputs, self.outputs, self.ws = inputs, outputs, ws
+        dev = ws.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            run()                                            # warm-up outside the capture (function attributes, caches)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            run()
+
+    def replay(self):
+        self.graph.replay()
+
+
 class _Holder(nn.Module):
     """Plain container that reproduces the reference module tree so state_dict keys line up."""
 
@@ -290,6 +312,10 @@ class AudioCodec(nn.Module):
         self._native: Optional[NativeCodec] = None
         self._native_version = -1
         self._version = 0
+        # CUDA graph per bucket: calls of at most `graph_max_batch` windows replay a captured graph of the padded chain
+        self.graph_max_batch = int(os.environ.get("SWC_GRAPH_MAX_BATCH", 4))
+        self._graphs: Dict[tuple, _GraphBucket] = {}
+        self.graph_replays = 0
 
     # ------------------------------------------------------------------ config / weights
     @staticmethod
@@ -332,11 +358,21 @@ class AudioCodec(nn.Module):
             raise RuntimeError(f"SimWhisper-Codec B200 path runs on CUDA tensors only (got {device}); no CPU fallback")
         if self._native is None or self._native_version != self._version or self._native.device != torch.device(
                 "cuda", device.index if device.index is not None else torch.cuda.current_device()):
+            self._graphs.clear()                             # captured graphs hold pointers into the old weight slab
             nat = NativeCodec(self.precision)
             nat.set_state(self.state_dict())
             nat.finalize(device)
             self._native, self._native_version = nat, self._version
         return self._native
+
+    def _bucket(self, key, build):
+        b = self._graphs.get(key)
+        if b is None:
+            if len(self._graphs) >= 32:                      # bounded: drop the oldest bucket
+                self._graphs.pop(next(iter(self._graphs)))
+            b = self._graphs[key] = build()
+        self.graph_replays += 1
+        return b
 
     def pack_preview(self) -> NativeCodec:
         """Host-only packing (no GPU needed): used by CPU tests of the weight layout."""
@@ -361,6 +397,8 @@ class AudioCodec(nn.Module):
         host_lens (Python ints, when the caller knows them) lets the bf16 path skip the padded tokens of every window."""
         nat = self._native_for(x2d.device)
         N = x2d.shape[0]
+        if 0 < N <= self.graph_max_batch and not torch.cuda.is_current_stream_capturing():
+            return self._tokenize_graph(nat, x2d, lens, want_zq)
         codes = torch.empty((8, N, 375), dtype=torch.int32, device=x2d.device)
         zq = torch.empty((N, 32, 375), dtype=torch.float32, device=x2d.device) if want_zq else None
         clens = torch.empty(N, dtype=torch.int64, device=x2d.device)
@@ -385,10 +423,65 @@ class AudioCodec(nn.Module):
                 codes[:, s:s + n] = c_part
         return codes, zq, clens
 
+    def _tokenize_graph(self, nat, x2d, lens, want_zq):
+        """small batches: the padded chain of this (batch, zq) bucket as one graph launch (results identical to the eager
+        and to the packed-token paths, which are bit-equal to each other)."""
+        dev, N, L = x2d.device, x2d.shape[0], min(x2d.shape[1], 480000)
+
+        def build():
+            x = torch.zeros((N, 480000), dtype=torch.float32, device=dev)
+            ln = torch.zeros(N, dtype=torch.int64, device=dev)
+            codes = torch.empty((8, N, 375), dtype=torch.int32, device=dev)
+            zq = torch.empty((N, 32, 375), dtype=torch.float32, device=dev) if want_zq else None
+            clens = torch.empty(N, dtype=torch.int64, device=dev)
+            need = int(nat.lib.swc_workspace_bytes(nat.handle, _lib.STAGE["tokenize"], N, 3000))
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+
+            def run():
+                _lib.check(nat.lib.swc_tokenize(nat.handle, _ptr(x), x.stride(0), x.shape[1], _ptr(ln), N, _ptr(codes), _ptr(zq),
+                                                _ptr(clens), _ptr(ws), C.c_size_t(ws.numel()), _stream(dev)), "swc_tokenize")
+            return _GraphBucket(run, (x, ln), (codes, zq, clens), ws)
+
+        b = self._bucket(("tokenize", dev.index, N, bool(want_zq)), build)
+        x, ln = b.inputs
+        x[:, :L].copy_(x2d[:, :L])                           # samples beyond an item's length are never read
+        ln.copy_(lens.clamp(max=L))
+        b.replay()
+        codes, zq, clens = b.outputs
+        return codes.clone(), (None if zq is None else zq.clone()), clens.clone()
+
+    def _detokenize_graph(self, nat, codes, lens):
+        dev = codes.device
+        _, N, Tc = codes.shape
+        i64 = codes.dtype == torch.int64
+
+        def build():
+            c = torch.zeros((8, N, Tc), dtype=codes.dtype, device=dev)
+            ln = torch.zeros(N, dtype=torch.int64, device=dev)
+            wav = torch.empty((N, 1280 * Tc), dtype=torch.float32, device=dev)
+            olens = torch.empty(N, dtype=torch.int64, device=dev)
+            need = int(nat.lib.swc_workspace_bytes(nat.handle, _lib.STAGE["detokenize"], N, Tc))
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+
+            def run():
+                _lib.check(nat.lib.swc_detokenize(nat.handle, _ptr(c), int(i64), _ptr(ln), N, Tc, _ptr(wav), _ptr(olens), _ptr(ws),
+                                                  C.c_size_t(ws.numel()), _stream(dev)), "swc_detokenize")
+            return _GraphBucket(run, (c, ln), (wav, olens), ws)
+
+        b = self._bucket(("detokenize", dev.index, N, Tc, i64), build)
+        c, ln = b.inputs
+        c.copy_(codes)
+        ln.copy_(lens)
+        b.replay()
+        wav, olens = b.outputs
+        return wav.clone(), olens.clone()
+
     def _detokenize(self, codes: torch.Tensor, lens: torch.Tensor, host_lens=None):
         """codes (8,N,T') int32/int64 cuda -> wav (N, 1280 T'), out lens."""
         nat = self._native_for(codes.device)
         _, N, Tc = codes.shape
+        if 0 < N <= self.graph_max_batch and Tc > 0 and not torch.cuda.is_current_stream_capturing():
+            return self._detokenize_graph(nat, codes, lens)
         wav = torch.empty((N, 1280 * Tc), dtype=torch.float32, device=codes.device)
         olens = torch.empty(N, dtype=torch.int64, device=codes.device)
         mb = self.max_batch

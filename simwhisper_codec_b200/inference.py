@@ -15,7 +15,7 @@ import yaml
 
 from .audiocodec.model import AudioCodec
 from .bitstream import pack_codes
-from .utils.helpers import find_audio_files, load_audio, save_audio, set_logging
+from .utils.helpers import can_decode, find_audio_files, load_audio, save_audio, set_logging
 
 _DEFAULT_CFG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "config", "SimWhisperCodec.yaml")
 
@@ -29,7 +29,8 @@ def main(argv=None) -> int:
     ap.add_argument("--batch_size", type=int, default=8)
     ap.add_argument("--input_dir", type=str, default="input_wavs")
     ap.add_argument("--output_dir", type=str, default="output_wavs")
-    ap.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32", "bf16x3"])
+    ap.add_argument("--precision", type=str, default="bf16x3", choices=["bf16x3", "bf16", "fp32"],
+                    help="bf16x3: parity-grade tensor-core mode (default); bf16: throughput mode; fp32: CUDA-core reference arithmetic")
     ap.add_argument("--codes_dir", type=str, default=None, help="also write <name>.swc code streams here")
     ap.add_argument("--random_init", action="store_true", help="deterministic random weights instead of a checkpoint")
     args = ap.parse_args(argv)
@@ -46,6 +47,10 @@ def main(argv=None) -> int:
     generator.eval()
 
     audio_paths = find_audio_files(input_dir=args.input_dir)
+    skipped = [p for p in audio_paths if not can_decode(p)]
+    for p in skipped:
+        logging.warning(f"Skipping {p}: no decoder for this format here (RIFF/WAVE is built in; flac / mp3 need soundfile or torchaudio)")
+    audio_paths = [p for p in audio_paths if p not in skipped]
     os.makedirs(args.output_dir, exist_ok=True)
     if args.codes_dir:
         os.makedirs(args.codes_dir, exist_ok=True)

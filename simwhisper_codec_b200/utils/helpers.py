@@ -140,16 +140,35 @@ def resample(wav: torch.Tensor, orig_freq: int, new_freq: int) -> torch.Tensor:
 def load_audio(audio_path: str, target_sample_rate: int, device="cpu") -> torch.Tensor:
     """reference utils/helpers.py:77-93 — mono mix, resample, shape (1, 1, time) float32."""
     ext = os.path.splitext(audio_path)[1].lower()
-    if ext != ".wav":
-        raise RuntimeError(f"{audio_path}: only RIFF/WAVE input is supported by the built-in reader "
-                           "(flac/mp3 need an external decoder; torchaudio's file backends are absent in this image)")
-    x, rate = read_wav(audio_path)
-    wav = torch.from_numpy(x).to(device)
+    if ext == ".wav":
+        x, rate = read_wav(audio_path)
+        wav = torch.from_numpy(x).to(device)
+    else:
+        wav, rate = _decode_with_external_backend(audio_path)
+        wav = wav.to(device)
     if wav.shape[0] > 1:
         wav = wav.mean(dim=0, keepdim=True)
     if rate != target_sample_rate:
         wav = resample(wav, rate, target_sample_rate)
     return wav.reshape(1, 1, -1).contiguous()
+
+
+def _decode_with_external_backend(audio_path: str):
+    """flac / mp3 (the reference reads them through torchaudio.load, utils/helpers.py:83): use soundfile or torchaudio when
+    one of them works in this environment, else raise (the built-in reader only knows RIFF/WAVE)."""
+    try:
+        import soundfile as sf
+        data, rate = sf.read(audio_path, dtype="float32", always_2d=True)
+        return torch.from_numpy(data.T.copy()), int(rate)
+    except Exception:
+        pass
+    try:
+        import torchaudio
+        wav, rate = torchaudio.load(audio_path)
+        return wav.to(torch.float32), int(rate)
+    except Exception as e:
+        raise RuntimeError(f"{audio_path}: only RIFF/WAVE input is supported by the built-in reader and no external decoder "
+                           f"(soundfile / torchaudio) is usable here: {str(e)[:120]}")
 
 
 def save_audio(audio_outpath: str, audio_out, sample_rate: int) -> None:
@@ -166,3 +185,17 @@ def find_audio_files(input_dir: str) -> List[str]:
         out.extend(glob.glob(os.path.join(input_dir, "**", ext), recursive=True))
     logging.info(f"Found {len(out)} audio files in {input_dir}")
     return sorted(out)
+
+
+def can_decode(audio_path: str) -> bool:
+    """True for RIFF/WAVE, and for flac / mp3 when an external decoder is importable; the CLI skips (with a warning) what
+    cannot be decoded instead of aborting the whole directory on the first such file."""
+    if os.path.splitext(audio_path)[1].lower() == ".wav":
+        return True
+    for mod in ("soundfile", "torchaudio"):
+        try:
+            __import__(mod)
+            return True
+        except Exception:
+            continue
+    return False

@@ -427,3 +427,28 @@ def test_overlap_other_than_default_fp32(model32, sd_ex):
         total = sum(c.numel() for c in codes)
         flips = sum((c.cpu().long() != r.long()).sum().item() for c, r in zip(codes, ref_codes))
         assert flips / total < 1e-3, (ov, flips, total)
+
+
+def test_cuda_graph_buckets_equal_eager(gen_params, sd_ex, sd_plain):
+    """Calls of a few windows replay a CUDA graph captured per (stage, batch, frames) bucket; the results are those of the
+    eager path bit for bit, a second call with other data reuses the bucket, and new weights drop the captured graphs."""
+    m = AudioCodec(gen_params, precision="bf16")
+    m.load_state_dict(sd_ex)
+    eager = AudioCodec(gen_params, precision="bf16")
+    eager.load_state_dict(sd_ex)
+    eager.graph_max_batch = 0
+    for rep, n in enumerate([(160000, 48123), (479999, 200000)]):
+        w = [synthetic_wave(9700 + rep * 10 + i, k) for i, k in enumerate(n)]
+        a = m.encode(w)["codes_list"]
+        b = eager.encode(w)["codes_list"]
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+        ya = m.decode(a)["syn_wav_list"]
+        yb = eager.decode(b)["syn_wav_list"]
+        assert all(torch.equal(x, y) for x, y in zip(ya, yb))
+    assert m.graph_replays >= 4 and eager.graph_replays == 0
+    n_buckets = len(m._graphs)
+    assert 2 <= n_buckets <= 8              # one per (stage, windows, frames) shape met above
+    m.load_state_dict(sd_plain)
+    eager.load_state_dict(sd_plain)
+    w = [synthetic_wave(9750, 160000)]
+    assert torch.equal(m.encode(w)["codes_list"][0], eager.encode(w)["codes_list"][0])      # re-captured on the new weights
