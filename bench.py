@@ -177,8 +177,9 @@ def main():
     ap.add_argument("--no-parity-leg", action="store_true",
                     help="skip the extra measurement of the parity-grade precision (bf16x3) at N = 1")
     ap.add_argument("--no-check", action="store_true", help="skip the output check of the timed configuration against bf16x3")
-    ap.add_argument("--sharded-api", default="auto", choices=["auto", "on", "off"],
-                    help="also run ShardedCodec.encode+decode on BASELINE configs[3] / a scaled configs[4] (auto: when N > 1)")
+    ap.add_argument("--sharded-api", default="on", choices=["on", "off"],
+                    help="also run ShardedCodec.encode+decode on BASELINE configs[3] (fixed job: strong scaling over N) and a "
+                         "configs[4] scaled to 4 ten-minute items per GPU")
     args = ap.parse_args()
 
     # stdout carries exactly one JSON line: anything libraries print meanwhile (NCCL's version banner, ...) goes to stderr
@@ -394,7 +395,7 @@ def main():
     # ---- BASELINE configs[3] / [4] through the sharded public API (windows dealt to the ranks, codes all-gathered, waveforms
     #      gathered to rank 0): valid audio-seconds per second, host planning and copies included
     sharded_api = None
-    if args.sharded_api == "on" or (args.sharded_api == "auto" and world > 1):
+    if args.sharded_api == "on" and args.precision == "bf16":
         from simwhisper_codec_b200.parallel import ShardedCodec
         if world == 1 and not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

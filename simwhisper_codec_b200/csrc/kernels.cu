@@ -19,65 +19,80 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, float eps, int nb,
                                                         int t_in, int t_out, const long long* __restrict__ lens) {
   constexpr int C = NCH * 256;
+  constexpr int RW = 2;                                               // rows per warp: both rows' loads are in flight together
   constexpr bool kPlanes = std::is_same<TO, bf16_planes>::value;     // rows of (hi | lo) bf16 planes, C columns each
   using TE = typename std::conditional<kPlanes, bf16, TO>::type;
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= (long long)nb * t_out) return;
-  const int b = (int)((unsigned)row / (unsigned)t_out), t = (int)row - b * t_out;     // nb * t_out < 2^31 (checked by the launcher)
-  TE* o = reinterpret_cast<TE*>(out) + row * (kPlanes ? 2 * C : C);
-  const bool in_range = t < t_in;
-  // the length is fetched together with the row, not before it: a row load that waits for lens[b] pays the L2 latency
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RW;
+  const long long n_rows = (long long)nb * t_out;
+  if (row0 >= n_rows) return;
+  float v[RW][NCH][8];
+  bool exists[RW], in_range[RW], live[RW];
+  long long irow[RW];
+  // the length is fetched together with the rows, not before them: a row load that waits for lens[b] pays the L2 latency
   // twice (rows beyond the length are then read for nothing; variable-length batches run the packed path instead)
-  const long long len_b = (in_range && lens) ? lens[b] : (long long)t_in;
-  const long long irow = ((long long)b * t_in + t) * C;
-  float v[NCH][8];
-  if (in_range) {
+  long long len_b[RW];
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const long long row = row0 + r;
+    exists[r] = row < n_rows;
+    const int b = (int)((unsigned)(exists[r] ? row : row0) / (unsigned)t_out);     // nb * t_out < 2^31 (checked by the launcher)
+    const int t = (int)((exists[r] ? row : row0) - (long long)b * t_out);
+    in_range[r] = exists[r] && t < t_in;
+    len_b[r] = (in_range[r] && lens) ? lens[b] : (long long)t_in;
+    irow[r] = ((long long)b * t_in + t) * C;
+    if (in_range[r]) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int c0 = (c * 32 + lane) * 8;
+        load8(in + irow[r] + c0, v[r][c]);
+        if (delta) {      // fused residual add: h <- h + delta (the GEMM that produced delta has no residual epilogue)
+          float dv[8];
+          load8(delta + irow[r] + c0, dv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[r][c][j] += dv[j];
+          if (h_out) store8(h_out + irow[r] + c0, v[r][c]);
+        }
+      }
+    }
+    live[r] = in_range[r] && (long long)t < len_b[r];
+  }
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    if (!exists[r]) continue;
+    TE* o = reinterpret_cast<TE*>(out) + (row0 + r) * (kPlanes ? 2 * C : C);
+    if (!live[r]) {
+      float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        store8(o + (c * 32 + lane) * 8, z);
+        if constexpr (kPlanes) store8(o + C + (c * 32 + lane) * 8, z);
+      }
+      continue;
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[r][c][j];
+    const float mean = warp_sum(sum) * (1.0f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { float dlt = v[r][c][j] - mean; sq = fmaf(dlt, dlt, sq); }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / C) + eps);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int c0 = (c * 32 + lane) * 8;
-      load8(in + irow + c0, v[c]);
-      if (delta) {      // fused residual add: h <- h + delta (the GEMM that produced delta has no residual epilogue)
-        float dv[8];
-        load8(delta + irow + c0, dv);
+      float g[8], bt[8], res[8];
+      load8(gamma + c0, g);
+      load8(beta + c0, bt);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[c][j] += dv[j];
-        if (h_out) store8(h_out + irow + c0, v[c]);
-      }
+      for (int j = 0; j < 8; ++j) res[j] = (v[r][c][j] - mean) * rstd * g[j] + bt[j];
+      if constexpr (kPlanes) store8_planes(o + c0, C, res);
+      else store8(o + c0, res);
     }
-  }
-  const bool live = in_range && (long long)t < len_b;
-  if (!live) {
-    float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      store8(o + (c * 32 + lane) * 8, z);
-      if constexpr (kPlanes) store8(o + C + (c * 32 + lane) * 8, z);
-    }
-    return;
-  }
-  float sum = 0.f;
-#pragma unroll
-  for (int c = 0; c < NCH; ++c)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sum += v[c][j];
-  const float mean = warp_sum(sum) * (1.0f / C);
-  float sq = 0.f;
-#pragma unroll
-  for (int c = 0; c < NCH; ++c)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { float dlt = v[c][j] - mean; sq = fmaf(dlt, dlt, sq); }
-  const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / C) + eps);
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int c0 = (c * 32 + lane) * 8;
-    float g[8], bt[8], r[8];
-    load8(gamma + c0, g);
-    load8(beta + c0, bt);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = (v[c][j] - mean) * rstd * g[j] + bt[j];
-    if constexpr (kPlanes) store8_planes(o + c0, C, r);
-    else store8(o + c0, r);
   }
 }
 
@@ -87,7 +102,7 @@ static int layernorm_t(const float* in, const float* delta, float* h_out, void* 
   const long long rows = (long long)nb * t_out;
   SWC_REQUIRE(rows < (1ll << 31), "layernorm: too many rows (%lld)", rows);
   const int warps = 8;
-  dim3 grid((unsigned)ceil_div_ll(rows, warps));
+  dim3 grid((unsigned)ceil_div_ll(rows, warps * 2));      // two rows per warp
   ProfScope ps(KC_LAYERNORM, s);
   if (C == 768) layernorm_kernel<TO, 3><<<grid, warps * 32, 0, s>>>(in, delta, h_out, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
   else if (C == 512) layernorm_kernel<TO, 2><<<grid, warps * 32, 0, s>>>(in, delta, h_out, (TO*)out, g, b, eps, nb, t_in, t_out, lens);
