@@ -543,13 +543,24 @@ class AudioCodec(nn.Module):
             return torch.zeros((self.num_groups, 0, 375), dtype=torch.int32, device=device)
         width = max(j.n_valid for j in jobs)
         x = torch.zeros((len(jobs), width), dtype=torch.float32, device=device)
-        on_dev = {}                                   # every utterance crosses the bus once, windows are cut on the device
+        # An utterance whose windows are (nearly) all in this batch crosses the bus once and is cut on the device; when only a
+        # few of its windows are here (long items sharded over ranks) only those slices are uploaded, not the whole item.
+        hop = (self.max_audio_seconds - 10) * self.input_sample_rate
+        mine: Dict[int, int] = {}
+        for j in jobs:
+            mine[j.item] = mine.get(j.item, 0) + 1
+        on_dev = {}
         for k, j in enumerate(jobs):
-            w = on_dev.get(j.item)
-            if w is None:
-                w = on_dev[j.item] = torch.as_tensor(wav_list[j.item]).reshape(-1).to(device=device, dtype=torch.float32,
-                                                                                      non_blocking=True)
-            x[k, : j.n_valid] = w[j.start:j.start + j.n_valid]
+            src = wav_list[j.item]
+            n_windows = max(1, -(-int(len(src)) // hop))
+            if 3 * mine[j.item] >= 2 * n_windows:
+                w = on_dev.get(j.item)
+                if w is None:
+                    w = on_dev[j.item] = torch.as_tensor(src).reshape(-1).to(device=device, dtype=torch.float32, non_blocking=True)
+                x[k, : j.n_valid] = w[j.start:j.start + j.n_valid]
+            else:
+                x[k, : j.n_valid] = torch.as_tensor(src).reshape(-1)[j.start:j.start + j.n_valid].to(
+                    device=device, dtype=torch.float32, non_blocking=True)
         wl = torch.tensor([j.n_valid for j in jobs], dtype=torch.int64).to(device, non_blocking=True)
         return self._tokenize(x, wl, want_zq=False, host_lens=[j.n_valid for j in jobs])[0]
 
