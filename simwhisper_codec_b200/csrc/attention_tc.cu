@@ -7,10 +7,12 @@
 //                 O_i += P_i V_j    UMMA M128 N64  K16 x8, A = P_i (bf16) from TMEM, B = V_j MN-major from shared memory
 //               one issuer per tile: each blocks only on its own tile's barriers (a single issuer either serialises the
 //               two warpgroups or pays ~150 cycles per polled barrier), and S runs one key block ahead of P V.
-//   warps 3-6   softmax warpgroup of query tile 0 (one thread = one query row = one TMEM lane)
-//   warps 7-10  softmax warpgroup of query tile 1
-//               (SPLIT = 2, the default: two threads share a row, 8 warps per tile, warps 3-10 / 11-18; the halves of a row
-//               exchange their maximum and their sum through shared memory behind a 64-thread named barrier of their own)
+//   warp 3      idle (keeps the producer / issuer warps a whole warpgroup for setmaxnreg)
+//   warps 4-11  softmax warps of query tile 0, warps 12-19 of query tile 1: two threads share a query row (= one TMEM lane),
+//               each owns 64 of the block's 128 score columns and 32 of the 64 output dims; the halves of a row exchange
+//               their maximum and their sum through shared memory behind a 64-thread named barrier of their own.
+//   Registers: launched at 96 per thread; warpgroup 0 shrinks to 48 and the four softmax warpgroups grow to 104 (setmaxnreg),
+//   which keeps 64 scores + 32 packed probabilities + the loop state of a softmax thread out of local memory.
 //
 // The two tiles ping-pong: while one warpgroup exponentiates S_i(j) the tensor core computes S_{1-i} / P V of the other.
 // Per tile and key block a softmax thread reads its 128 scores from TMEM, takes the row maximum, and only when the

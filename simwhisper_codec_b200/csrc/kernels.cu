@@ -2,6 +2,7 @@
 // FSQ, layout conversion, log-mel pre/post passes, iSTFT overlap-add.  All are HBM-streaming
 // kernels: coalesced along the channel (contiguous) dimension, 16/32-byte vector accesses, fp32 math.
 #include <algorithm>
+#include <cstdlib>
 
 #include <type_traits>
 
@@ -96,6 +97,138 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Streaming form for the common case (contiguous rows, no length mask, no fused add): a producer warp streams 8-row chunks
+// into a 4-stage shared-memory ring with bulk async copies (cp.async.bulk + mbarrier transaction bytes), eight consumer warps
+// normalise one row each straight from shared memory.  The loads are decoupled from the arithmetic: up to 4 x 24 KB per CTA
+// (two CTAs per SM) are in flight whatever the consumers are doing.  Same lane -> channel mapping and the same order of
+// additions as layernorm_kernel: results are bit-identical.
+// ------------------------------------------------------------------------------------------------
+namespace lnstream {
+constexpr int kRows = 8, kStages = 4, kThreads = 32 * (kRows + 1);
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+}  // namespace lnstream
+
+template <typename TO, int NCH>
+__global__ void __launch_bounds__(lnstream::kThreads, 2) layernorm_stream_kernel(const float* __restrict__ in, TO* __restrict__ out,
+                                                                                const float* __restrict__ gamma,
+                                                                                const float* __restrict__ beta, float eps, long long n_rows) {
+  using namespace lnstream;
+  constexpr int C = NCH * 256;
+  constexpr bool kPlanes = std::is_same<TO, bf16_planes>::value;
+  using TE = typename std::conditional<kPlanes, bf16, TO>::type;
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  float* ring = reinterpret_cast<float*>(ln_smem);                                  // [kStages][kRows][C]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ln_smem + (size_t)kStages * kRows * C * 4);
+  uint64_t* empty = full + kStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kRows); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long n_chunks = (n_rows + kRows - 1) / kRows;
+  if (warp == kRows) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+        const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+        mbar_wait(&empty[st], ph ^ 1);
+        const long long r0 = c * kRows;
+        const uint32_t bytes = (uint32_t)(min((long long)kRows, n_rows - r0) * C * 4);
+        mbar_expect_tx(&full[st], bytes);
+        bulk_load(ring + (size_t)st * kRows * C, in + r0 * C, bytes, &full[st]);
+      }
+    }
+    return;
+  }
+  float g[NCH][8], bt[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    load8(gamma + (c * 32 + lane) * 8, g[c]);
+    load8(beta + (c * 32 + lane) * 8, bt[c]);
+  }
+  uint32_t it = 0;
+  for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+    const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+    const long long row = c * kRows + warp;
+    mbar_wait(&full[st], ph);
+    if (row < n_rows) {
+      const float* src = ring + ((size_t)st * kRows + warp) * C;
+      float v[NCH][8];
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) load8(src + (k * 32 + lane) * 8, v[k]);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[k][j];
+      const float mean = warp_sum(sum) * (1.0f / C);
+      float sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { float dlt = v[k][j] - mean; sq = fmaf(dlt, dlt, sq); }
+      const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / C) + eps);
+      TE* o = reinterpret_cast<TE*>(out) + row * (kPlanes ? 2 * C : C);
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int c0 = (k * 32 + lane) * 8;
+        float res[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) res[j] = (v[k][j] - mean) * rstd * g[k][j] + bt[k][j];
+        if constexpr (kPlanes) store8_planes(o + c0, C, res);
+        else store8(o + c0, res);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+}
+
+template <typename TO, int NCH>
+static int layernorm_stream_launch(const float* in, void* out, const float* g, const float* b, float eps, long long rows, cudaStream_t s) {
+  constexpr int C = NCH * 256;
+  const int smem = lnstream::kStages * lnstream::kRows * C * 4 + 2 * lnstream::kStages * 8;
+  auto kern = layernorm_stream_kernel<TO, NCH>;
+  SWC_TRY(ensure_dynamic_smem((const void*)kern, smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long chunks = (rows + lnstream::kRows - 1) / lnstream::kRows;
+  const int grid = (int)std::min<long long>(chunks, 2ll * sms);
+  ProfScope ps(KC_LAYERNORM, s);
+  kern<<<grid, lnstream::kThreads, smem, s>>>(in, (TO*)out, g, b, eps, rows);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <typename TO>
 static int layernorm_t(const float* in, const float* delta, float* h_out, void* out, const float* g, const float* b, float eps,
                        int nb, int t_in, int t_out, int C, const long long* lens, cudaStream_t s) {
@@ -113,6 +246,18 @@ static int layernorm_t(const float* in, const float* delta, float* h_out, void* 
 
 int layernorm(const float* in, const float* delta, float* h_out, void* out, int out_type, const float* gamma,
               const float* beta, float eps, int nb, int t_in, int t_out, int C, const long long* lens, cudaStream_t s) {
+  static const bool stream_ok = [] { const char* e = getenv("SWC_LN_STREAM"); return !(e && e[0] == '0'); }();
+  if (stream_ok && !delta && !lens && t_in == t_out && ((uintptr_t)in & 15) == 0 && (long long)nb * t_in >= 4096 && (C == 768 || C == 512)) {
+    const long long rows = (long long)nb * t_in;
+    if (C == 768) {
+      if (out_type == 0) return layernorm_stream_launch<float, 3>(in, out, gamma, beta, eps, rows, s);
+      if (out_type == 2) return layernorm_stream_launch<bf16_planes, 3>(in, out, gamma, beta, eps, rows, s);
+      return layernorm_stream_launch<bf16, 3>(in, out, gamma, beta, eps, rows, s);
+    }
+    if (out_type == 0) return layernorm_stream_launch<float, 2>(in, out, gamma, beta, eps, rows, s);
+    if (out_type == 2) return layernorm_stream_launch<bf16_planes, 2>(in, out, gamma, beta, eps, rows, s);
+    return layernorm_stream_launch<bf16, 2>(in, out, gamma, beta, eps, rows, s);
+  }
   if (out_type == 0) return layernorm_t<float>(in, delta, h_out, out, gamma, beta, eps, nb, t_in, t_out, C, lens, s);
   if (out_type == 2) return layernorm_t<bf16_planes>(in, delta, h_out, out, gamma, beta, eps, nb, t_in, t_out, C, lens, s);
   return layernorm_t<bf16>(in, delta, h_out, out, gamma, beta, eps, nb, t_in, t_out, C, lens, s);
