@@ -314,6 +314,7 @@ class AudioCodec(nn.Module):
         self._version = 0
         # CUDA graph per bucket: calls of at most `graph_max_batch` windows replay a captured graph of the padded chain
         self.graph_max_batch = int(os.environ.get("SWC_GRAPH_MAX_BATCH", 4))
+        self.api_chunk = int(os.environ.get("SWC_API_CHUNK", 96))      # windows per upload / launch chunk of encode()
         self._graphs: Dict[tuple, _GraphBucket] = {}
         self.graph_replays = 0
 
@@ -538,31 +539,40 @@ class AudioCodec(nn.Module):
 
     # ---- window batches (shared by the single-GPU API below and parallel.ShardedCodec)
     def encode_jobs(self, wav_list, jobs, device) -> torch.Tensor:
-        """Tokenize the given (item, start, n_valid) windows as one batch -> codes (8, len(jobs), 375) int32."""
+        """Tokenize the given (item, start, n_valid) windows -> codes (8, len(jobs), 375) int32.
+
+        The windows go through in chunks of at most `api_chunk`: a chunk's kernels are only enqueued (nothing synchronises),
+        so the host -> device copies of the next chunk - pageable user memory, synchronous for the host - run while the GPU
+        works on the current one; only the first chunk's upload is exposed."""
         if not jobs:
             return torch.zeros((self.num_groups, 0, 375), dtype=torch.int32, device=device)
-        width = max(j.n_valid for j in jobs)
-        x = torch.zeros((len(jobs), width), dtype=torch.float32, device=device)
-        # An utterance whose windows are (nearly) all in this batch crosses the bus once and is cut on the device; when only a
+        # An utterance whose windows are (nearly) all in this call crosses the bus once and is cut on the device; when only a
         # few of its windows are here (long items sharded over ranks) only those slices are uploaded, not the whole item.
         hop = (self.max_audio_seconds - 10) * self.input_sample_rate
         mine: Dict[int, int] = {}
         for j in jobs:
             mine[j.item] = mine.get(j.item, 0) + 1
         on_dev = {}
-        for k, j in enumerate(jobs):
-            src = wav_list[j.item]
-            n_windows = max(1, -(-int(len(src)) // hop))
-            if 3 * mine[j.item] >= 2 * n_windows:
-                w = on_dev.get(j.item)
-                if w is None:
-                    w = on_dev[j.item] = torch.as_tensor(src).reshape(-1).to(device=device, dtype=torch.float32, non_blocking=True)
-                x[k, : j.n_valid] = w[j.start:j.start + j.n_valid]
-            else:
-                x[k, : j.n_valid] = torch.as_tensor(src).reshape(-1)[j.start:j.start + j.n_valid].to(
-                    device=device, dtype=torch.float32, non_blocking=True)
-        wl = torch.tensor([j.n_valid for j in jobs], dtype=torch.int64).to(device, non_blocking=True)
-        return self._tokenize(x, wl, want_zq=False, host_lens=[j.n_valid for j in jobs])[0]
+        chunk = max(1, min(self.max_batch, self.api_chunk))
+        parts = []
+        for c0 in range(0, len(jobs), chunk):
+            part = jobs[c0:c0 + chunk]
+            width = max(j.n_valid for j in part)
+            x = torch.zeros((len(part), width), dtype=torch.float32, device=device)
+            for k, j in enumerate(part):
+                src = wav_list[j.item]
+                n_windows = max(1, -(-int(len(src)) // hop))
+                if 3 * mine[j.item] >= 2 * n_windows:
+                    w = on_dev.get(j.item)
+                    if w is None:
+                        w = on_dev[j.item] = torch.as_tensor(src).reshape(-1).to(device=device, dtype=torch.float32, non_blocking=True)
+                    x[k, : j.n_valid] = w[j.start:j.start + j.n_valid]
+                else:
+                    x[k, : j.n_valid] = torch.as_tensor(src).reshape(-1)[j.start:j.start + j.n_valid].to(
+                        device=device, dtype=torch.float32, non_blocking=True)
+            wl = torch.tensor([j.n_valid for j in part], dtype=torch.int64).to(device, non_blocking=True)
+            parts.append(self._tokenize(x, wl, want_zq=False, host_lens=[j.n_valid for j in part])[0])
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
 
     def decode_jobs(self, codes_list, jobs, device) -> torch.Tensor:
         """Detokenize decode windows that share one pad length T' -> wav (len(jobs), 1280 T')."""

@@ -38,7 +38,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     else:
@@ -56,7 +55,7 @@ def main():
         # correctness on a subset (every rank takes part in the sharded calls)
         sub = wavs[: args.check]
         c_sh = sc.encode(sub, device=dev)["codes_list"]
-        w_sh = sc.decode(c_sh, device=dev)["syn_wav_list"]
+        w_sh = sc.decode(c_sh, device=dev)["syn_wav_list"]          # stitched on rank 0 only
         ok = None
         if rank == 0:
             c_1 = model.encode(sub, device=dev)["codes_list"]
