@@ -34,8 +34,8 @@ GF_TOTAL = 1311.86
 GF_ATTN = 24 * 6.912
 GF_MEL = 1.061
 GF_IDFT = 2.465
-# DRAM traffic of the tcgen05 GEMM class per window, from the committed ncu launch list (profiles/r1_ncu_launches_v7_final.md)
-GEMM_DRAM_GB_PER_WINDOW = 2.66
+# DRAM traffic of the tcgen05 GEMM class per window, from the committed ncu launch list (profiles/r2_ncu_launches.md)
+GEMM_DRAM_GB_PER_WINDOW = 2.65
 GF_TC_GEMM = GF_TOTAL - GF_ATTN - 0.096              # contractions that run on the tcgen05 GEMM kernels: everything but
                                                        # attention and the 80-bin mel filterbank (the forward and inverse DFTs
                                                        # run as split-bf16 GEMMs; their algorithmic FLOPs are counted once)
@@ -356,7 +356,7 @@ def main():
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                 "traffic": GEMM_DRAM_GB_PER_WINDOW * 1e9 * B / max(cls_n["gemm_tcgen05"], 1),
                 "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of the gemm_tc* launches of one "
-                                "step under ncu, profiles/r1_ncu_launches_v7_final.md, averaged per launch)",
+                                "step under ncu, profiles/r2_ncu_launches.md, averaged per launch)",
                 "peak_source": peak_src,
                 "algorithmic_gflop_per_window": GF_TC_GEMM, "windows_per_step": B, "launches_per_step": cls_n["gemm_tcgen05"],
                 "avg_launch_ms": gemm_ms / max(cls_n["gemm_tcgen05"], 1),

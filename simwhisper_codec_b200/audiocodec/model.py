@@ -360,11 +360,25 @@ class AudioCodec(nn.Module):
         if self._native is None or self._native_version != self._version or self._native.device != torch.device(
                 "cuda", device.index if device.index is not None else torch.cuda.current_device()):
             self._graphs.clear()                             # captured graphs hold pointers into the old weight slab
+            self._graph_ws = None
             nat = NativeCodec(self.precision)
             nat.set_state(self.state_dict())
             nat.finalize(device)
             self._native, self._native_version = nat, self._version
         return self._native
+
+    def _graph_workspace(self, nat, need: int, device) -> torch.Tensor:
+        """One scratch buffer shared by all captured graphs of this model (they replay on one stream, one after the other),
+        sized once for the largest bucket (graph_max_batch full windows); growing it would drop the graphs captured against
+        the old buffer."""
+        ws = getattr(self, "_graph_ws", None)
+        if ws is None or ws.numel() < need or ws.device != device:
+            n = max(1, self.graph_max_batch)
+            need = max(need, int(nat.lib.swc_workspace_bytes(nat.handle, _lib.STAGE["tokenize"], n, 3000)),
+                       int(nat.lib.swc_workspace_bytes(nat.handle, _lib.STAGE["detokenize"], n, 375)))
+            self._graphs.clear()
+            self._graph_ws = ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return ws
 
     def _bucket(self, key, build):
         b = self._graphs.get(key)
@@ -435,8 +449,7 @@ class AudioCodec(nn.Module):
             codes = torch.empty((8, N, 375), dtype=torch.int32, device=dev)
             zq = torch.empty((N, 32, 375), dtype=torch.float32, device=dev) if want_zq else None
             clens = torch.empty(N, dtype=torch.int64, device=dev)
-            need = int(nat.lib.swc_workspace_bytes(nat.handle, _lib.STAGE["tokenize"], N, 3000))
-            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            ws = self._graph_workspace(nat, int(nat.lib.swc_workspace_bytes(nat.handle, _lib.STAGE["tokenize"], N, 3000)), dev)
 
             def run():
                 _lib.check(nat.lib.swc_tokenize(nat.handle, _ptr(x), x.stride(0), x.shape[1], _ptr(ln), N, _ptr(codes), _ptr(zq),
@@ -461,8 +474,7 @@ class AudioCodec(nn.Module):
             ln = torch.zeros(N, dtype=torch.int64, device=dev)
             wav = torch.empty((N, 1280 * Tc), dtype=torch.float32, device=dev)
             olens = torch.empty(N, dtype=torch.int64, device=dev)
-            need = int(nat.lib.swc_workspace_bytes(nat.handle, _lib.STAGE["detokenize"], N, Tc))
-            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            ws = self._graph_workspace(nat, int(nat.lib.swc_workspace_bytes(nat.handle, _lib.STAGE["detokenize"], N, Tc)), dev)
 
             def run():
                 _lib.check(nat.lib.swc_detokenize(nat.handle, _ptr(c), int(i64), _ptr(ln), N, Tc, _ptr(wav), _ptr(olens), _ptr(ws),
