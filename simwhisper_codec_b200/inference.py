@@ -60,7 +60,8 @@ def main(argv=None) -> int:
     for i in range(0, len(audio_paths), bs):
         batch_paths = audio_paths[i:i + bs]
         logging.info(f"Processing batch {i // bs + 1}/{(len(audio_paths) + bs - 1) // bs}, files: {batch_paths}")
-        wav_list = [load_audio(p, target_sample_rate=generator.input_sample_rate).squeeze().to(device) for p in batch_paths]
+        # decoded on the host, moved to the device as it is, resampled to 16 kHz there (utils.helpers.resample is device-agnostic)
+        wav_list = [load_audio(p, target_sample_rate=generator.input_sample_rate, device=device).squeeze() for p in batch_paths]
         logging.info(f"Successfully loaded {len(wav_list)} audio files with lengths {[len(w) for w in wav_list]} samples")
         codes_list = generator.encode(wav_list, overlap_seconds=10, device=device)["codes_list"]
         logging.info(f"Encoding completed, code lengths: {[c.shape[-1] for c in codes_list]}")
