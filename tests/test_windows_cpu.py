@@ -196,3 +196,33 @@ def test_sharded_equals_single_process_gloo():
             outs[j.item][off:off + n] = w[k, :n]
     for a, b in zip(outs, wav2):
         assert torch.equal(a, b)
+
+
+def test_plans_match_reference_loops_randomised():
+    """Seeded sweep over batch compositions and overlaps (including hops that are not multiples of 1280 samples and items
+    shorter than one code frame): the flat encode / decode plans must reproduce the reference's chunk loops exactly."""
+    g = torch.Generator().manual_seed(2024)
+    fake = FakeCodec()
+    for trial in range(40):
+        overlap = int(torch.randint(0, 26, (), generator=g))
+        n_items = int(torch.randint(1, 6, (), generator=g))
+        lens = [int(torch.randint(0, 1_300_000, (), generator=g)) if float(torch.rand((), generator=g)) > 0.2
+                else int(torch.randint(0, 3000, (), generator=g)) for _ in range(n_items)]
+        if max(lens) == 0:
+            continue
+        wavs = [torch.randn(n, generator=g) for n in lens]
+        jobs = windows.plan_encode(lens, overlap)
+        ours = fake.stitch_codes(fake.encode_jobs(wavs, jobs, "cpu"), lens, jobs, overlap)
+        ref = _reference_style_encode(fake, wavs, overlap)
+        assert [tuple(c.shape) for c in ours] == [tuple(c.shape) for c in ref], (trial, overlap, lens)
+        assert all(torch.equal(a, b) for a, b in zip(ours, ref)), (trial, overlap, lens)
+        codes_list = [torch.randint(0, 2016, (8, max(1, n // 1280)), generator=g) for n in lens]
+        L = [c.shape[-1] for c in codes_list]
+        outs = [torch.zeros(n * 1280) for n in L]
+        for _, dj in windows.plan_decode(L, overlap).items():
+            w = fake.decode_jobs(codes_list, dj, "cpu")
+            for k, j in enumerate(dj):
+                off, n = windows.decode_keep(j, overlap)
+                outs[j.item][off:off + n] = w[k, :n]
+        for a, b in zip(outs, _reference_style_decode(fake, codes_list, overlap)):
+            assert torch.equal(a, b), (trial, overlap, L)
