@@ -21,6 +21,7 @@ constexpr float kRescaleThreshold = 8.0f;                // log2 units
 // kRegsSoftmax (128 x 48 + 512 x 104 = 58 K): the softmax threads hold 64 scores, 32 packed probabilities and the loop state.
 constexpr int kThreads = 128 + 512;
 constexpr int kRegsIssue = 48, kRegsSoftmax = 104;
+constexpr int kRegsSoftmax1 = 208;      // one thread per query row (experiment): 384 threads launched at 168 registers
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 

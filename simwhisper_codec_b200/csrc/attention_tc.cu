@@ -45,7 +45,7 @@ constexpr int kSmemBytes = kOutOff + 2 * kTileBytes + 1024;
 constexpr uint32_t kColS = 0, kColP = 256, kColO = 384;
 
 template <int SPLIT, typename TAB>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(128 + 256 * SPLIT, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, const __grid_constant__ TAB tab) {
   constexpr bool kRagged = std::is_same<TAB, RaggedTable>::value;
   extern __shared__ uint8_t smem_raw[];
@@ -82,7 +82,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
   const int D3 = 3 * p.H * HD;
 
   if (warp < 4) setmaxnreg_dec<kRegsIssue>();
-  else setmaxnreg_inc<kRegsSoftmax>();
+  else setmaxnreg_inc<SPLIT == 2 ? kRegsSoftmax : kRegsSoftmax1>();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -243,14 +243,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
       float m_used = -INFINITY, l = 0.f;
       if (tracer) trace_stamp(p, tslot, tr);                 // A: item decoded
       const uint32_t sa = lane_addr + kColS + i * 128 + part * NC;
+      constexpr int NV = NC / 32;                          // 32-register score vectors per thread (2 or 4)
       for (int j = 0; j < it.n_kt; ++j) {
         mbar_wait(&s_full[i], s_cnt & 1);
         if (tracer) trace_stamp(p, tslot, tr);               // B: S ready
         ++s_cnt;
         tc_fence_after();
-        uint32_t s0[32], s1[32];
-        tmem_ld32(sa, s0);
-        tmem_ld32(sa + 32, s1);
+        uint32_t sv[NV][32];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) tmem_ld32(sa + 32 * v, sv[v]);
         tmem_ld_wait();
         if (tracer && p.fine) trace_stamp(p, tslot, tr);               // B1: S in registers
         tc_fence_before();
@@ -261,21 +262,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         const int valid = it.len - j * KT - part * NC;      // valid keys among this thread's columns (may be <= 0)
         if (valid < NC) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if (c >= valid) s0[c] = 0xff800000u;   // -inf
-            if (c + 32 >= valid) s1[c] = 0xff800000u;
-          }
+          for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (v * 32 + c >= valid) sv[v][c] = 0xff800000u;   // -inf
         }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
-          mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(s0[c + 1]), __uint_as_float(s1[c + 1])));
-          mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(s0[c + 2]), __uint_as_float(s1[c + 2])));
-          mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(s0[c + 3]), __uint_as_float(s1[c + 3])));
-        }
+        for (int v = 0; v < NV; v += 2)
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(sv[v][c]), __uint_as_float(sv[v + 1][c])));
+            mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(sv[v][c + 1]), __uint_as_float(sv[v + 1][c + 1])));
+            mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(sv[v][c + 2]), __uint_as_float(sv[v + 1][c + 2])));
+            mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(sv[v][c + 3]), __uint_as_float(sv[v + 1][c + 3])));
+          }
         float mxl = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kLog2e;
-        {                                             // combine the parts' maxima (double-buffered exchange slots)
+        if constexpr (SPLIT > 1) {                    // combine the parts' maxima (double-buffered exchange slots)
           const uint32_t slot = xch + (x_cnt & 1) * (SPLIT * QT * 4);
           ++x_cnt;
           sts_f32(slot + part * QT * 4, mxl);
@@ -286,22 +289,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         float scale = 1.0f;
         const bool grow = mxl > m_used + kRescaleThreshold;     // always true for j == 0 (m_used = -inf)
         if (grow) { scale = ex2(m_used - mxl); m_used = mxl; }   // j == 0: scale = 0, l = 0, O not yet written
-        uint32_t pk0[16], pk1[16];
+        uint32_t pk[NV][16];
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
-        auto exp_half = [&](const uint32_t (&sh)[32], uint32_t (&pk)[16]) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
-            const float p0 = ex2(fmaf(__uint_as_float(sh[c]), kLog2e, -m_used));
-            const float p1 = ex2(fmaf(__uint_as_float(sh[c + 1]), kLog2e, -m_used));
-            const float p2 = ex2(fmaf(__uint_as_float(sh[c + 2]), kLog2e, -m_used));
-            const float p3 = ex2(fmaf(__uint_as_float(sh[c + 3]), kLog2e, -m_used));
+            const float p0 = ex2(fmaf(__uint_as_float(sv[v][c]), kLog2e, -m_used));
+            const float p1 = ex2(fmaf(__uint_as_float(sv[v][c + 1]), kLog2e, -m_used));
+            const float p2 = ex2(fmaf(__uint_as_float(sv[v][c + 2]), kLog2e, -m_used));
+            const float p3 = ex2(fmaf(__uint_as_float(sv[v][c + 3]), kLog2e, -m_used));
             sum[0] += p0; sum[1] += p1; sum[2] += p2; sum[3] += p3;
-            pk[c >> 1] = pack2(p0, p1);
-            pk[(c >> 1) + 1] = pack2(p2, p3);
+            pk[v][c >> 1] = pack2(p0, p1);
+            pk[v][(c >> 1) + 1] = pack2(p2, p3);
           }
-        };
-        exp_half(s0, pk0);
-        exp_half(s1, pk1);
         l = fmaf(l, scale, (sum[0] + sum[1]) + (sum[2] + sum[3]));   // this part's share of the row sum
         if (tracer && p.fine) trace_stamp(p, tslot, tr);               // B3: exponentials done
         if (j > 0) {
@@ -310,19 +311,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           tc_fence_after();
           if (__any_sync(0xffffffffu, grow)) {          // same rows, hence the same votes, in every part's warp
             const uint32_t oa = lane_addr + kColO + i * 64 + part * ND;
-            uint32_t o[ND];
-            tmem_ld_n(oa, o);
-            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < ND; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * scale);
-            tmem_st_n(oa, o);
+            for (int h2 = 0; h2 < ND / 32; ++h2) {
+              uint32_t o[32];
+              tmem_ld32(oa + 32 * h2, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * scale);
+              tmem_st32(oa + 32 * h2, o);
+            }
           }
         }
         if (tracer && p.fine) trace_stamp(p, tslot, tr);               // B4: previous P V done (P slot free)
         {
           const uint32_t pa = lane_addr + kColP + i * 64 + part * (NC / 2);
-          tmem_st16(pa, pk0);
-          tmem_st16(pa + 16, pk1);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) tmem_st16(pa + 16 * v, pk[v]);
           tmem_st_wait();
         }
         tc_fence_before();
@@ -336,7 +340,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
       ++o_cnt;
       tc_fence_after();
       uint32_t o[ND];
-      tmem_ld_n(lane_addr + kColO + i * 64 + part * ND, o);
+      if constexpr (ND == 32) {
+        tmem_ld32(lane_addr + kColO + i * 64 + part * ND, o);
+      } else {
+        tmem_ld64(lane_addr + kColO + i * 64, o);
+      }
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -422,6 +430,8 @@ int attention_tc_launch(const bf16* qkv, bf16* out, const long long* lens, long 
     kern<<<grid, threads, kSmemBytes, s>>>(tm, p, tab);
     return 0;
   };
+  // two threads per query row.  (One thread per row, SPLIT = 1 with 208 registers per softmax thread, is correct and 4 %
+  // slower: a single warp per scheduler and tile reaches only ~62 % of the MUFU rate, tools/micro/mufu_rate.cu.)
   const int rc = go(attention_tc_kernel<2, TAB>, kThreads);      // two threads per query row (the one-thread-per-row form is gone)
   if (rc) return rc;
   SWC_CHECK_CUDA(cudaGetLastError());
