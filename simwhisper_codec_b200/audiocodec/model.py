@@ -110,18 +110,22 @@ class _GraphBucket:
 
     def __init__(self, run, inputs, outputs, ws):
         self.inputs, self.outputs, self.ws = inputs, outputs, ws
-        dev = ws.device
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            run()                                            # warm-up outside the capture (function attributes, caches)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            run()
+        self.dev = dev = ws.device
+        # capture and replay with the buffers' device current: torch captures on (and replays into) a stream of the CURRENT
+        # device, and a model on cuda:1 called while cuda:0 is current would otherwise capture an empty graph
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                run()                                        # warm-up outside the capture (function attributes, caches)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                run()
 
     def replay(self):
-        self.graph.replay()
+        with torch.cuda.device(self.dev):
+            self.graph.replay()
 
 
 class _Holder(nn.Module):
@@ -317,6 +321,7 @@ class AudioCodec(nn.Module):
         self.api_chunk = int(os.environ.get("SWC_API_CHUNK", 96))      # windows per upload / launch chunk of encode()
         self._graphs: Dict[tuple, _GraphBucket] = {}
         self.graph_replays = 0
+        self._copy_streams: Dict[int, "torch.cuda.Stream"] = {}      # per device: host -> device copies of encode()
 
     # ------------------------------------------------------------------ config / weights
     @staticmethod
@@ -550,62 +555,65 @@ class AudioCodec(nn.Module):
         return {"y": wav[:, None, :], "output_length": olens}
 
     # ---- window batches (shared by the single-GPU API below and parallel.ShardedCodec)
+    def _copy_stream(self, device) -> "torch.cuda.Stream":
+        device = torch.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        st = self._copy_streams.get(idx)
+        if st is None:
+            st = self._copy_streams[idx] = torch.cuda.Stream(device=idx)
+        return st
+
     def encode_jobs(self, wav_list, jobs, device) -> torch.Tensor:
         """Tokenize the given (item, start, n_valid) windows -> codes (8, len(jobs), 375) int32.
 
-        The windows go through in chunks of at most `api_chunk`: a chunk's kernels are only enqueued (nothing synchronises),
-        so the host -> device copies of the next chunk - pageable user memory, synchronous for the host - run while the GPU
-        works on the current one; only the first chunk's upload is exposed."""
+        Every window is copied host -> device exactly once, straight into its row of the chunk's input batch, on a copy
+        stream of its own; the windows go through in chunks of at most `api_chunk`, each chunk's kernels wait only for
+        that chunk's copies (an event), and nothing synchronises with the host.  From pinned memory the copies are
+        asynchronous DMA and run under the kernels of the chunk before; from pageable memory the driver stages them
+        through the host (the call then blocks while it copies, the GPU still overlaps).  A rank of a sharded job
+        uploads only the windows it computes."""
         if not jobs:
             return torch.zeros((self.num_groups, 0, 375), dtype=torch.int32, device=device)
-        # An utterance whose windows are (nearly) all in this call crosses the bus once and is cut on the device; when only a
-        # few of its windows are here (long items sharded over ranks) only those slices are uploaded, not the whole item.
-        hop = (self.max_audio_seconds - 10) * self.input_sample_rate
-        mine: Dict[int, int] = {}
-        for j in jobs:
-            mine[j.item] = mine.get(j.item, 0) + 1
-        on_dev = {}
+        device = torch.device(device)
         chunk = max(1, min(self.max_batch, self.api_chunk))
-        parts = []
-        for c0 in range(0, len(jobs), chunk):
-            part = jobs[c0:c0 + chunk]
-            width = max(j.n_valid for j in part)
-            x = torch.zeros((len(part), width), dtype=torch.float32, device=device)
-            for k, j in enumerate(part):
-                src = wav_list[j.item]
-                n_windows = max(1, -(-int(len(src)) // hop))
-                if 3 * mine[j.item] >= 2 * n_windows:
-                    w = on_dev.get(j.item)
-                    if w is None:
-                        w = on_dev[j.item] = torch.as_tensor(src).reshape(-1).to(device=device, dtype=torch.float32, non_blocking=True)
-                    x[k, : j.n_valid] = w[j.start:j.start + j.n_valid]
-                else:
-                    x[k, : j.n_valid] = torch.as_tensor(src).reshape(-1)[j.start:j.start + j.n_valid].to(
-                        device=device, dtype=torch.float32, non_blocking=True)
-            wl = torch.tensor([j.n_valid for j in part], dtype=torch.int64).to(device, non_blocking=True)
-            parts.append(self._tokenize(x, wl, want_zq=False, host_lens=[j.n_valid for j in part])[0])
-        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+        cur = torch.cuda.current_stream(device)
+        side = self._copy_stream(device)
+        parts = [jobs[c0:c0 + chunk] for c0 in range(0, len(jobs), chunk)]
+        # input batches first (allocated on the compute stream; the copy stream starts behind everything queued so far, so
+        # a recycled block is never overwritten while an earlier kernel still reads it)
+        xs = [torch.empty((len(p), max(j.n_valid for j in p)), dtype=torch.float32, device=device) for p in parts]
+        flat = {}
+        side.wait_stream(cur)
+        outs = []
+        for part, x in zip(parts, xs):
+            with torch.cuda.stream(side):
+                for k, j in enumerate(part):
+                    src = flat.get(j.item)
+                    if src is None:
+                        src = flat[j.item] = torch.as_tensor(wav_list[j.item]).reshape(-1)
+                    x[k, : j.n_valid].copy_(src[j.start:j.start + j.n_valid], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            cur.wait_event(ev)
+            hl = [j.n_valid for j in part]
+            wl = torch.tensor(hl, dtype=torch.int64).to(device, non_blocking=True)
+            outs.append(self._tokenize(x, wl, want_zq=False, host_lens=hl)[0])      # samples beyond n_valid are never read
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
 
     def decode_jobs(self, codes_list, jobs, device) -> torch.Tensor:
         """Detokenize decode windows that share one pad length T' -> wav (len(jobs), 1280 T')."""
         Tp = jobs[0].pad_len
-        # longest window first: with the lengths in descending order the library runs Vocos (46 % of the FLOPs, no
-        # length masking in the reference) only over each run's valid frames plus its receptive-field halo instead of
-        # over all T' frames of every window; samples beyond a window's halo are left unwritten (callers keep valid ones)
-        order = sorted(range(len(jobs)), key=lambda k: -jobs[k].n_valid)
+        # the host knows every window's valid length: the library runs the transformer stack on the packed valid tokens and
+        # Vocos (46 % of the FLOPs, no length masking in the reference) on each window's valid frames plus its
+        # receptive-field halo, all windows packed into one batch of rows; samples beyond a window's halo are left
+        # unwritten (callers keep the valid ones)
         ct = torch.zeros((self.num_groups, len(jobs), Tp), dtype=torch.int64, device=device)
-        for r, k in enumerate(order):
-            j = jobs[k]
-            ct[:, r, : j.n_valid] = torch.as_tensor(codes_list[j.item])[:, j.start:j.start + j.n_valid].to(
+        for k, j in enumerate(jobs):
+            ct[:, k, : j.n_valid] = torch.as_tensor(codes_list[j.item])[:, j.start:j.start + j.n_valid].to(
                 device=device, dtype=torch.int64, non_blocking=True)
-        hl = [jobs[k].n_valid for k in order]
+        hl = [j.n_valid for j in jobs]
         cl = torch.tensor(hl, dtype=torch.int64).to(device, non_blocking=True)
-        wav = self._detokenize(ct, cl, host_lens=hl)[0]
-        if order == list(range(len(jobs))):
-            return wav
-        inv = torch.empty(len(jobs), dtype=torch.int64)
-        inv[torch.tensor(order)] = torch.arange(len(jobs))
-        return wav.index_select(0, inv.to(device, non_blocking=True))
+        return self._detokenize(ct, cl, host_lens=hl)[0]
 
     @torch.inference_mode()
     def encode(self, wav_list, overlap_seconds=10, device=torch.device("cuda")):

@@ -346,13 +346,18 @@ __device__ __forceinline__ float dw_rstd(float var_eps) {
   else return 1.0f / sqrtf(var_eps);
 }
 
-template <typename TO, bool HAS_DELTA>
+// TAB = DenseRows: item b owns rows [b T, b T + T).  TAB = RaggedTable: item b owns rows [off[b], off[b] + len[b]) of a
+// packed buffer (items of different lengths back to back, Vocos over valid frames + halo only); rows outside an item are
+// the convolution's zero padding in both layouts, so neighbouring items never see each other.
+struct DenseRows {};
+template <typename TO, bool HAS_DELTA, typename TAB>
 __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ delta,
                                                                    float* __restrict__ x_out, const float* __restrict__ w,
                                                                    const float* __restrict__ bias,
                                                                    const float* __restrict__ gamma,
                                                                    const float* __restrict__ beta, float eps,
-                                                                   TO* __restrict__ out, int T, int strip) {
+                                                                   TO* __restrict__ out, int T_dense, int strip,
+                                                                   const __grid_constant__ TAB tab) {
   constexpr int C = 512, R = kDwRows;
   constexpr bool kPlanes = std::is_same<TO, bf16_planes>::value;     // rows of (hi | lo) bf16 planes (bf16x3 mode: exact rstd)
   using TE = typename std::conditional<kPlanes, bf16, TO>::type;
@@ -363,11 +368,21 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
   const int c0 = tid * 4;
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * strip;
+  int T;
+  long long row0;
+  if constexpr (std::is_same<TAB, RaggedTable>::value) {
+    T = tab.len[b];
+    row0 = tab.off[b];
+    if (t0 >= T) return;                  // strips beyond this item's rows (the grid spans the longest item)
+  } else {
+    T = T_dense;
+    row0 = (long long)b * T;
+  }
   const int t_end = min(T, t0 + strip);
-  const float* xb = x + (long long)b * T * C + c0;
-  const float* db = HAS_DELTA ? delta + (long long)b * T * C + c0 : nullptr;
-  float* xo = HAS_DELTA ? x_out + (long long)b * T * C + c0 : nullptr;
-  TE* ob = reinterpret_cast<TE*>(out) + (long long)b * T * (kPlanes ? 2 * C : C) + c0;
+  const float* xb = x + row0 * C + c0;
+  const float* db = HAS_DELTA ? delta + row0 * C + c0 : nullptr;
+  float* xo = HAS_DELTA ? x_out + row0 * C + c0 : nullptr;
+  TE* ob = reinterpret_cast<TE*>(out) + row0 * (kPlanes ? 2 * C : C) + c0;
 
 #pragma unroll
   for (int k = 0; k < 7; ++k) *reinterpret_cast<float4*>(sw + k * C + c0) = *reinterpret_cast<const float4*>(w + k * C + c0);
@@ -469,26 +484,41 @@ __global__ void __launch_bounds__(kDwThreads, 4) dwconv7_ln_kernel(const float* 
   }
 }
 
-int dwconv7_ln(const float* x, const float* delta, float* x_out, const float* w7c, const float* bias, const float* gamma,
-               const float* beta, float eps, void* out, int out_type, int nb, int T, int C, cudaStream_t s) {
-  SWC_REQUIRE(C == 512, "dwconv7_ln: only C=512 is built (got %d)", C);
-  SWC_REQUIRE(!delta || (x_out && x_out != x), "dwconv7_ln: fused residual needs a distinct output stream buffer");
+namespace {
+template <typename TAB>
+int dwconv7_ln_launch(const float* x, const float* delta, float* x_out, const float* w7c, const float* bias, const float* gamma,
+                      const float* beta, float eps, void* out, int out_type, int nb, int T, const TAB& tab, cudaStream_t s) {
   ProfScope ps(KC_DWCONV_LN, s);
   // strips of 64 rows (9 % halo re-reads, served by the L2) when that gives every SM many blocks, else 32
   const int strip = ((long long)nb * ceil_div(T, 64) >= 16 * 148) ? 64 : 32;
   dim3 grid(ceil_div(T, strip), nb);
   if (out_type == 2) {
-    if (delta) dwconv7_ln_kernel<bf16_planes, true><<<grid, kDwThreads, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (bf16_planes*)out, T, strip);
-    else dwconv7_ln_kernel<bf16_planes, false><<<grid, kDwThreads, 0, s>>>(x, nullptr, nullptr, w7c, bias, gamma, beta, eps, (bf16_planes*)out, T, strip);
+    if (delta) dwconv7_ln_kernel<bf16_planes, true, TAB><<<grid, kDwThreads, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (bf16_planes*)out, T, strip, tab);
+    else dwconv7_ln_kernel<bf16_planes, false, TAB><<<grid, kDwThreads, 0, s>>>(x, nullptr, nullptr, w7c, bias, gamma, beta, eps, (bf16_planes*)out, T, strip, tab);
   } else if (out_type == 0) {
-    if (delta) dwconv7_ln_kernel<float, true><<<grid, kDwThreads, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (float*)out, T, strip);
-    else dwconv7_ln_kernel<float, false><<<grid, kDwThreads, 0, s>>>(x, nullptr, nullptr, w7c, bias, gamma, beta, eps, (float*)out, T, strip);
+    if (delta) dwconv7_ln_kernel<float, true, TAB><<<grid, kDwThreads, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (float*)out, T, strip, tab);
+    else dwconv7_ln_kernel<float, false, TAB><<<grid, kDwThreads, 0, s>>>(x, nullptr, nullptr, w7c, bias, gamma, beta, eps, (float*)out, T, strip, tab);
   } else {
-    if (delta) dwconv7_ln_kernel<bf16, true><<<grid, kDwThreads, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (bf16*)out, T, strip);
-    else dwconv7_ln_kernel<bf16, false><<<grid, kDwThreads, 0, s>>>(x, nullptr, nullptr, w7c, bias, gamma, beta, eps, (bf16*)out, T, strip);
+    if (delta) dwconv7_ln_kernel<bf16, true, TAB><<<grid, kDwThreads, 0, s>>>(x, delta, x_out, w7c, bias, gamma, beta, eps, (bf16*)out, T, strip, tab);
+    else dwconv7_ln_kernel<bf16, false, TAB><<<grid, kDwThreads, 0, s>>>(x, nullptr, nullptr, w7c, bias, gamma, beta, eps, (bf16*)out, T, strip, tab);
   }
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+}  // namespace
+
+int dwconv7_ln(const float* x, const float* delta, float* x_out, const float* w7c, const float* bias, const float* gamma,
+               const float* beta, float eps, void* out, int out_type, int nb, int T, int C, cudaStream_t s) {
+  SWC_REQUIRE(C == 512, "dwconv7_ln: only C=512 is built (got %d)", C);
+  SWC_REQUIRE(!delta || (x_out && x_out != x), "dwconv7_ln: fused residual needs a distinct output stream buffer");
+  return dwconv7_ln_launch(x, delta, x_out, w7c, bias, gamma, beta, eps, out, out_type, nb, T, DenseRows{}, s);
+}
+
+int dwconv7_ln_ragged(const float* x, const float* w7c, const float* bias, const float* gamma, const float* beta, float eps,
+                      void* out, int out_type, const RaggedTable& tab, int C, cudaStream_t s) {
+  SWC_REQUIRE(C == 512, "dwconv7_ln_ragged: only C=512 is built (got %d)", C);
+  SWC_REQUIRE(tab.nb > 0 && tab.nb <= kMaxRagged && tab.t_max > 0, "dwconv7_ln_ragged: bad table");
+  return dwconv7_ln_launch(x, nullptr, nullptr, w7c, bias, gamma, beta, eps, out, out_type, tab.nb, tab.t_max, tab, s);
 }
 
 // ================================================================================================
@@ -831,8 +861,9 @@ int mel_finalize(const float* logmel, const float* item_max, int nb, float* mel_
 // iSTFT overlap-add with "same" padding (reference modules.py:861-884): n_fft 640, hop 160.
 // out[s] = sum_t frames[t][p-160t] / sum_t w^2[p-160t],  p = s + 240, t in the <=4 overlapping frames.
 // ================================================================================================
-__global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ win_sq, int T,
-                                                        float* __restrict__ wav, long long wav_stride) {
+template <typename TAB>
+__global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ win_sq, int T_dense,
+                                                        float* __restrict__ wav, long long wav_stride, const __grid_constant__ TAB tab) {
   // one thread = 4 consecutive output samples: hop, trim and frame length are multiples of 4, so the four samples sit in
   // the same (<= 4) frames and every access is a float4
   __shared__ __align__(16) float w2[640];
@@ -840,6 +871,10 @@ __global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict_
   __syncthreads();
   const int b = blockIdx.y;
   const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  int T;
+  long long row0;
+  if constexpr (std::is_same<TAB, RaggedTable>::value) { T = tab.len[b]; row0 = tab.off[b]; }
+  else { T = T_dense; row0 = (long long)b * T; }
   const int L = 160 * T;
   if (sidx >= L) return;
   const int p = sidx + 240;
@@ -848,7 +883,7 @@ __global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict_
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), env = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int t = t_lo; t <= t_hi; ++t) {
     const int n = p - 160 * t;
-    const float4 f = *reinterpret_cast<const float4*>(frames + ((long long)b * T + t) * 640 + n);
+    const float4 f = *reinterpret_cast<const float4*>(frames + (row0 + t) * 640 + n);
     const float4 w = *reinterpret_cast<const float4*>(w2 + n);
     acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
     env.x += w.x; env.y += w.y; env.z += w.z; env.w += w.w;
@@ -859,7 +894,17 @@ int istft_ola(const float* frames, const float* win_sq, int nb, int T, float* wa
   SWC_REQUIRE(((uintptr_t)frames & 15) == 0 && ((uintptr_t)wav & 15) == 0 && wav_stride % 4 == 0, "istft_ola: buffers must be 16-byte aligned");
   dim3 grid(ceil_div(40 * T, 256), nb);
   ProfScope ps(KC_MISC, s);
-  istft_ola_kernel<<<grid, 256, 0, s>>>(frames, win_sq, T, wav, wav_stride);
+  istft_ola_kernel<DenseRows><<<grid, 256, 0, s>>>(frames, win_sq, T, wav, wav_stride, DenseRows{});
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+// packed frames: item b = rows [off[b], off[b] + len[b]) of `frames`, written to wav + b * wav_stride (160 len[b] samples)
+int istft_ola_ragged(const float* frames, const float* win_sq, const RaggedTable& tab, float* wav, long long wav_stride, cudaStream_t s) {
+  SWC_REQUIRE(((uintptr_t)frames & 15) == 0 && ((uintptr_t)wav & 15) == 0 && wav_stride % 4 == 0, "istft_ola_ragged: buffers must be 16-byte aligned");
+  SWC_REQUIRE(tab.nb > 0 && tab.nb <= kMaxRagged && tab.t_max > 0, "istft_ola_ragged: bad table");
+  dim3 grid(ceil_div(40 * tab.t_max, 256), tab.nb);
+  ProfScope ps(KC_MISC, s);
+  istft_ola_kernel<RaggedTable><<<grid, 256, 0, s>>>(frames, win_sq, 0, wav, wav_stride, tab);
   SWC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -939,6 +984,27 @@ __global__ void unpack_rows_kernel(const T* __restrict__ packed, T* __restrict__
   uint4* dst = reinterpret_cast<uint4*>(padded) + (long long)b * t_pad * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     dst[i] = i < valid ? src[i] : make_uint4(0, 0, 0, 0);
+}
+// the same for rows of `row_bytes` (a multiple of 16) of any type, and the rows between the items' ends and the next item's
+// start (off[b] + len[b] .. off[b + 1]) are written as zero: the packed Vocos input, whose 7-tap embedding convolution reads
+// up to three rows across an item's edges
+__global__ void pack_rows_gap_kernel(const uint4* __restrict__ padded, uint4* __restrict__ packed, const __grid_constant__ RaggedTable tab,
+                                     int t_pad, int G) {
+  const int b = blockIdx.y;
+  const long long valid = (long long)tab.len[b] * G, total = (long long)(tab.off[b + 1] - tab.off[b]) * G;
+  const uint4* src = padded + (long long)b * t_pad * G;
+  uint4* dst = packed + (long long)tab.off[b] * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = i < valid ? src[i] : make_uint4(0, 0, 0, 0);
+}
+int pack_rows_gap(const void* padded, void* packed, const RaggedTable& tab, int t_pad, int row_bytes, cudaStream_t s) {
+  SWC_REQUIRE(row_bytes % 16 == 0 && tab.nb > 0 && tab.t_max <= t_pad, "pack_rows_gap: bad shape");
+  const int G = row_bytes / 16;
+  dim3 grid((unsigned)std::max(1, std::min(64, ceil_div((tab.t_max + 8) * G, 256))), tab.nb);
+  ProfScope ps(KC_MISC, s);
+  pack_rows_gap_kernel<<<grid, 256, 0, s>>>((const uint4*)padded, (uint4*)packed, tab, t_pad, G);
+  SWC_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 int pack_rows(const float* padded, float* packed, const RaggedTable& tab, int t_pad, int C, cudaStream_t s) {
   SWC_REQUIRE(C % 4 == 0 && tab.nb > 0, "pack_rows: bad shape");

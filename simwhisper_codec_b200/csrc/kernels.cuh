@@ -69,6 +69,15 @@ int pack_rows(const float* padded, float* packed, const RaggedTable& tab, int t_
 // padded[b, t] = t < len[b] ? packed[off[b] + t] : 0 for t < t_pad   (dtype 0 fp32 / 1 bf16)
 int unpack_rows(const void* packed, void* padded, int dtype, const RaggedTable& tab, int t_pad, int C, cudaStream_t s);
 
+// packed rows with zeroed gaps: packed[off[b] + t] = padded[b, t] for t < len[b], rows off[b] + len[b] .. off[b + 1] - 1 = 0
+// (rows of row_bytes bytes, a multiple of 16; off[] may leave gaps between items)
+int pack_rows_gap(const void* padded, void* packed, const RaggedTable& tab, int t_pad, int row_bytes, cudaStream_t s);
+// dwconv7 + LayerNorm and the iSTFT overlap-add over packed items (item b = rows [off[b], off[b] + len[b]); rows outside an
+// item are zero padding, exactly as at the ends of a dense (nb, T) batch)
+int dwconv7_ln_ragged(const float* x, const float* w7c, const float* bias, const float* gamma, const float* beta, float eps,
+                      void* out, int out_type, const RaggedTable& tab, int C, cudaStream_t s);
+int istft_ola_ragged(const float* frames, const float* win_sq, const RaggedTable& tab, float* wav, long long wav_stride, cudaStream_t s);
+
 // fp32 SIMT flash attention over fused qkv rows (nb*T, 3*H*64): q pre-scaled. Keys >= lens[b] masked.
 int attention_simt(const void* qkv, int type, void* out, const long long* lens, int nb, int T, int H, cudaStream_t s);
 // bf16x3 mode: fp32-class flash attention on tcgen05 (attention_tc_x3.cu) over the (hi | lo) bf16 planes of the fp32 qkv rows

@@ -393,15 +393,16 @@ int decoder_cl(Ctx& c, float* h, const long long* lens, int nb, int T, void* mel
 // ------------------------------------------------------------------------------------------------
 // Vocos backbone + ISTFT head (reference modules.py:1492-1504, 1229-1248, 1064-1082, 831-886)
 // mel_cl (nb,Tv,128) act type -> wav fp32 (nb,160 Tv).  No length masking anywhere.
-// Tv_in / wav_stride (0 = dense): the caller may run only the first Tv frames of items that are Tv_in frames long; the
-// convolutions then see zeros beyond frame Tv - 1 exactly as at the end of a sequence (TMA zero fill / dwconv padding).
+// vt (optional): PACKED items.  mel_cl then holds vt->total rows, item b = rows [off[b], off[b] + len[b]) with at least three
+// zero rows between consecutive items (pack_rows_gap), every GEMM / LayerNorm runs over all rows as one batch, the depthwise
+// convolutions and the overlap-add take the item geometry from the table, and item b's 160 len[b] samples go to
+// wav + b * wav_stride.  Sizing (dry) runs pass extra_rows for the gap rows of the packed form.
 // ------------------------------------------------------------------------------------------------
-int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav, int Tv_in, long long wav_stride) {
+int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav, const RaggedTable* vt, long long wav_stride, int extra_rows) {
   const Model& m = *c.m;
-  if (Tv_in <= 0) Tv_in = Tv;
   if (wav_stride <= 0) wav_stride = 160ll * Tv;
   const int V = m.voc_dim, I = m.voc_inter, MP = m.mel_pitch, at = m.act_type();
-  const long long rows = (long long)nb * Tv;
+  const long long rows = vt ? (long long)vt->total : (long long)nb * Tv + extra_rows;
   const int NP = m.voc_head.N;
   const size_t mark = c.ws.mark();
   float* x = (float*)c.ws.alloc(rows * V * 4);       // fp32 residual stream; pwconv2 accumulates into it (x += gamma * (...))
@@ -414,16 +415,19 @@ int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav, int Tv_in, 
     void* g = region;
     float* e = (float*)region;     // embed output (fp32) lives in the region until the first LayerNorm
     {
-      GemmDesc d = base_desc(mel_cl, MP, (long long)Tv_in * MP, Tv, MP, Tv, nb, m.voc_embed);
+      // packed: one batch of `rows` rows; the taps of an item's first / last rows land in the zero rows between the items
+      GemmDesc d = vt ? base_desc(mel_cl, MP, 0, (int)rows, MP, (int)rows, 1, m.voc_embed)
+                      : base_desc(mel_cl, MP, (long long)Tv * MP, Tv, MP, Tv, nb, m.voc_embed);
       d.n_taps = 7; d.tap_k = MP;
       for (int k = 0; k < 7; ++k) { d.tap_row[k] = k - 3; d.tap_col[k] = 0; }
-      set_out(d, e, V, (long long)Tv * V);
+      set_out(d, e, V, vt ? 0 : (long long)Tv * V);
       SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
     }
-    SWC_TRY(layernorm(e, nullptr, nullptr, x, 0, m.voc_norm_g, m.voc_norm_b, 1e-6f, nb, Tv, Tv, V, nullptr, c.s));
+    SWC_TRY(layernorm(e, nullptr, nullptr, x, 0, m.voc_norm_g, m.voc_norm_b, 1e-6f, 1, (int)rows, (int)rows, V, nullptr, c.s));
     for (const VocosBlockW& B : m.voc_blocks) {
       const bool y_planes = x3_rowwise_planes(c, B.pw1);
-      SWC_TRY(dwconv7_ln(x, nullptr, nullptr, B.dw_w, B.dw_b, B.ln_g, B.ln_b, 1e-6f, y, y_planes ? 2 : at, nb, Tv, V, c.s));
+      if (vt) SWC_TRY(dwconv7_ln_ragged(x, B.dw_w, B.dw_b, B.ln_g, B.ln_b, 1e-6f, y, y_planes ? 2 : at, *vt, V, c.s));
+      else SWC_TRY(dwconv7_ln(x, nullptr, nullptr, B.dw_w, B.dw_b, B.ln_g, B.ln_b, 1e-6f, y, y_planes ? 2 : at, nb, Tv, V, c.s));
       const bool planes = x3_planes(c, B.pw1, B.pw2);      // bf16x3 mode: the 4096-wide hidden goes to pwconv2 as bf16 planes
       {
         GemmDesc d = base_desc(y, y_planes ? 2 * V : V, 0, (int)rows, V, (int)rows, 1, B.pw1);
@@ -442,7 +446,7 @@ int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav, int Tv_in, 
         SWC_TRY(run_gemm(c, d, EPI_STORE, at, 0));
       }
     }
-    SWC_TRY(layernorm(x, nullptr, nullptr, y, at, m.voc_final_g, m.voc_final_b, 1e-6f, nb, Tv, Tv, V, nullptr, c.s));
+    SWC_TRY(layernorm(x, nullptr, nullptr, y, at, m.voc_final_g, m.voc_final_b, 1e-6f, 1, (int)rows, (int)rows, V, nullptr, c.s));
     float* S = (float*)region;
     float* frames = S + rows * NP;
     const bool tc_idft = (at == 1 || m.x3()) && !c.force_simt && m.w_idft3 != nullptr;
@@ -468,7 +472,8 @@ int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav, int Tv_in, 
       set_out(d, frames, m.n_fft, 0);
       SWC_TRY(gemm_simt(d, EPI_STORE, 0, 0, c.s));
     }
-    SWC_TRY(istft_ola(frames, m.win_sq, nb, Tv, wav, wav_stride, c.s));
+    if (vt) SWC_TRY(istft_ola_ragged(frames, m.win_sq, *vt, wav, wav_stride, c.s));
+    else SWC_TRY(istft_ola(frames, m.win_sq, nb, Tv, wav, wav_stride, c.s));
   }
   c.ws.release(mark);
   return 0;
@@ -560,31 +565,36 @@ int detokenize_chain(Ctx& c, const float* zq_cl, const long long* code_lens, int
   SWC_TRY(decoder_cl(c, h, tok_lens, nb, T, mel_cl));
   // Vocos has no length masking (reference modules.py:1492-1504) but its receptive field is finite: an output sample
   // of frame t reads frames <= t + 1 of the last block, each of the 24 depthwise convolutions and the embedding add 3:
-  // everything a valid sample depends on lies below frame 8 len + 77.  When the caller passed host lengths in
-  // descending order (decode_jobs does), items are grouped into runs of similar length and each run computes only
-  // min(Tv, 8 len_max + 80) frames; the frames beyond see the cut as a sequence end, which can reach valid samples
-  // only from frame 8 len + 5 on.  Valid samples are bit-identical to the full-length computation.
-  bool bucketed = false;
-  if (c.rag != nullptr && c.rag->nb == nb && !c.dry && (at == 1 || m.x3())) {
-    bucketed = true;
-    for (int b = 1; b < nb; ++b) bucketed = bucketed && c.rag->len[b] <= c.rag->len[b - 1];
+  // everything a valid sample depends on lies below frame 8 len + 77.  When the caller passed host lengths, item b
+  // computes only need(b) = min(Tv, 8 len + 80) frames: the items' rows are packed back to back (eight zero rows between
+  // them for the embedding convolution's taps), every GEMM of the backbone runs once over all packed rows, and the
+  // depthwise convolutions / the overlap-add see each item's cut as a sequence end, which can reach valid samples only
+  // from frame 8 len + 5 on.  Valid samples are bit-identical to the full-length computation.
+  const bool packed = c.rag != nullptr && c.rag->nb == nb && (at == 1 || m.x3());
+  constexpr int kGap = 8;
+  void* mel_pk = nullptr;
+  if (c.dry || packed) {
+    mel_pk = c.ws.alloc((long long)nb * (Tv + kGap) * m.mel_pitch * esz(at));
+    SWC_TRY(c.ws.check());
   }
-  if (bucketed) {
+  if (c.dry) {
+    SWC_TRY(vocos_cl(c, mel_cl, nb, Tv, wav, nullptr, 0, nb * kGap));
+  } else if (packed) {
     // receptive field of a valid sample: 3 frames per depthwise convolution and for the embedding, + 1 for the overlap-add,
     // rounded up to 8 (24 ConvNeXt blocks: 77 -> 80); derived from the model so another depth cannot silently corrupt frames
     const int kHalo = (3 * ((int)m.voc_blocks.size() + 1) + 2 + 7) / 8 * 8;
-    constexpr long long kMinRows = 40000;            // >= two waves of 256-row tile pairs per GEMM launch
-    auto need = [&](int b) { return std::min(Tv, 2 * c.rag->len[b] + kHalo); };      // len = tokens = 4 x code frames
-    const size_t mel_row = (size_t)m.mel_pitch * esz(at);
-    for (int b0 = 0; b0 < nb;) {
-      const int tv = (need(b0) + 7) / 8 * 8 > Tv ? Tv : (need(b0) + 7) / 8 * 8;
-      int b1 = b0 + 1;
-      while (b1 < nb && ((long long)(b1 - b0) * tv < kMinRows || need(b1) * 10 >= tv * 8)) ++b1;
-      if ((long long)(nb - b1) * tv < kMinRows / 2) b1 = nb;                            // no tiny last run
-      SWC_TRY(vocos_cl(c, (const char*)mel_cl + (size_t)b0 * Tv * mel_row, b1 - b0, tv, wav + (long long)b0 * 160 * Tv, Tv,
-                       160ll * Tv));
-      b0 = b1;
+    RaggedTable vt;
+    vt.nb = nb; vt.total = 0; vt.t_max = 0;
+    for (int b = 0; b < nb; ++b) {
+      const int need = std::min(Tv, (2 * c.rag->len[b] + kHalo + 7) / 8 * 8);      // len = tokens = 4 x code frames
+      vt.len[b] = need;
+      vt.off[b] = vt.total;
+      vt.total += need + (b + 1 < nb ? kGap : 0);
+      vt.t_max = std::max(vt.t_max, need);
     }
+    vt.off[nb] = vt.total;
+    SWC_TRY(pack_rows_gap(mel_cl, mel_pk, vt, Tv, m.mel_pitch * (int)esz(at), c.s));
+    SWC_TRY(vocos_cl(c, mel_pk, nb, Tv, wav, &vt, 160ll * Tv));
   } else {
     SWC_TRY(vocos_cl(c, mel_cl, nb, Tv, wav));
   }

@@ -46,8 +46,10 @@ int downsample_fsq(Ctx& c, const void* enc_cl, const long long* code_lens, int n
                    float* latent_cf, float* zq_cl);
 int upsample_cl(Ctx& c, const float* zq_cl, int nb, int Tc, float* h);
 int decoder_cl(Ctx& c, float* h, const long long* lens, int nb, int T, void* mel_cl);
-// Tv frames of every item are computed; the items' rows are Tv_in frames apart in mel_cl and wav_stride floats apart in wav
-int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav, int Tv_in = 0, long long wav_stride = 0);
+// dense: Tv frames of each of the nb items; vt: packed items of different lengths (see pipeline.cu); wav rows are wav_stride
+// floats apart (0 = 160 Tv); extra_rows only enlarges the buffers of a sizing run
+int vocos_cl(Ctx& c, const void* mel_cl, int nb, int Tv, float* wav, const RaggedTable* vt = nullptr, long long wav_stride = 0,
+             int extra_rows = 0);
 int mel_frontend(Ctx& c, const float* wav, long long wav_stride, int wav_cols, const long long* lens, int nb,
                  float* mel_cf, void* mel_cl, long long* mel_lens);
 int tokenize_chain(Ctx& c, const float* wav, long long wav_stride, int wav_cols, const long long* lens, int nb,

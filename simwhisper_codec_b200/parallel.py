@@ -8,8 +8,9 @@ shards reproduce the single-GPU (= reference) result exactly.
 What travels:
   * encode: the codes of every window, 12 KB each — all-gathered, so every rank holds `codes_list` (decode() needs it
     on every rank, and it is four orders of magnitude less data than the audio);
-  * decode: waveforms (1.9 MB per window) go to ONE rank (`dst`, the caller's) with `dist.gather`, or nowhere
-    (`gather_wav=False`: every rank keeps the windows it decoded, e.g. to write them to disk itself).
+  * decode: the KEPT samples of every window (at most 20 s = 1.3 MB, packed into one flat buffer per rank) go to ONE
+    rank (`dst`, the caller's) with `dist.gather`, or nowhere (`gather_wav=False`: every rank keeps the windows it
+    decoded, e.g. to write them to disk itself).
 """
 from __future__ import annotations
 
@@ -38,18 +39,6 @@ def _all_gather_rows(local: torch.Tensor, counts: List[int], group) -> List[torc
     out = torch.empty((world * nmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)   # concatenated along dim 0
     dist.all_gather_into_tensor(out, _pad_rows(local, nmax), group=group)
     return [out[r * nmax: r * nmax + n] for r, n in enumerate(counts)]
-
-
-def _gather_rows(local: torch.Tensor, counts: List[int], group, dst: int) -> Optional[List[torch.Tensor]]:
-    """the same towards one rank: the list on `dst`, None elsewhere."""
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    if world == 1:
-        return [local]
-    nmax = max(counts) if counts else 0
-    send = _pad_rows(local, nmax)
-    bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
-    dist.gather(send, bufs, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
-    return [b[:n] for b, n in zip(bufs, counts)] if rank == dst else None
 
 
 class ShardedCodec:
@@ -111,14 +100,28 @@ class ShardedCodec:
                     off, n = windows.decode_keep(j, *keep_args)
                     local.append((j.item, off, wav[k, :n]))
                 continue
-            parts = _gather_rows(wav, [len(s) for s in shards], self.group, self.dst)
+            # only the samples that are kept travel: every rank packs the kept part of its windows into one flat buffer
+            # (all ranks know all jobs, hence every rank's total), rank dst receives world buffers of the largest total
+            keeps = [[windows.decode_keep(jobs[j], *keep_args) for j in s] for s in shards]
+            totals = [sum(n for _, n in ks) for ks in keeps]
+            send = torch.empty(max(totals), dtype=torch.float32, device=device)
+            if my_jobs:
+                torch._foreach_copy_(list(torch.split(send[: totals[rank]], [n for _, n in keeps[rank]])),
+                                     [wav[k, :n] for k, (_, n) in enumerate(keeps[rank])])
+            if world == 1:
+                bufs = [send]
+            else:
+                bufs = [torch.empty_like(send) for _ in range(world)] if on_dst else None
+                dist.gather(send, bufs, dst=dist.get_global_rank(self.group, self.dst) if self.group is not None else self.dst,
+                            group=self.group)
             if not on_dst:
                 continue
             for r, s in enumerate(shards):
-                for k, j in enumerate(s):
-                    off, n = windows.decode_keep(jobs[j], *keep_args)
+                pos = 0
+                for j, (off, n) in zip(s, keeps[r]):
                     dst_views.append(outs[jobs[j].item][off:off + n])
-                    src_views.append(parts[r][k, :n])
+                    src_views.append(bufs[r][pos:pos + n])
+                    pos += n
         if not gather_wav:
             return {"local": local}
         if on_dst and dst_views:

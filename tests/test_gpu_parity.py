@@ -272,6 +272,25 @@ def test_ragged_transformer_path_is_bit_identical(mode, model16, model_x3, monke
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3"])
+def test_packed_vocos_valid_samples_are_bit_identical(mode, model16, model_x3):
+    """With host-known lengths the detokenizer packs every window's valid frames + receptive-field halo into one batch of
+    rows (items of any length in any order, eight zero rows between them); the valid samples of every item must equal
+    the dense full-length computation bit for bit - including one-frame items, full-length items and items whose halo
+    is cut by the pad length."""
+    m = model16 if mode == "bf16" else model_x3
+    g = torch.Generator().manual_seed(77)
+    for Tc, lens in ((375, [375, 1, 200, 375, 7, 366, 365, 33, 120, 374, 2, 250]), (125, [125, 3, 64, 124, 1, 90]),
+                     (40, [int(v) for v in torch.randint(1, 41, (19,), generator=g)])):
+        n = len(lens)
+        codes = torch.stack([torch.randint(0, v, (n, Tc), generator=g) for v in (2016,) * 8]).cuda()
+        cl = torch.tensor(lens, dtype=torch.int64, device="cuda")
+        dense = m._detokenize(codes, cl)[0]
+        packed = m._detokenize(codes, cl, host_lens=lens)[0]
+        for b, L in enumerate(lens):
+            assert torch.equal(dense[b, : 1280 * L], packed[b, : 1280 * L]), (mode, Tc, b, L)
+
+
 def test_mel_bf16_mode_keeps_fp32_accuracy(model16):
     """In bf16 mode the log-mel front end runs its DFT on the tensor cores as a six-product split-bf16 GEMM with fp32
     accumulation; it must still meet the fp32 bound against the reference (mel max-abs-err <= 1e-4)."""
