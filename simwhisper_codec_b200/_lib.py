@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswc.so")
+# SWC_LIB_PATH: another build of the same library (development A/B runs); the product path is the in-tree libswc.so
+LIB_PATH = os.environ.get("SWC_LIB_PATH") or os.path.join(_HERE, "libswc.so")
 
 PRECISION = {"fp32": 0, "bf16": 1, "bf16x3": 2}
 KCLASS = ("gemm_tcgen05", "gemm_simt_fp32", "attention", "layernorm", "dwconv7_ln", "aa_snake", "other")
