@@ -120,7 +120,9 @@ class _GraphBucket:
                 run()                                        # warm-up outside the capture (function attributes, caches)
             torch.cuda.current_stream(dev).wait_stream(side)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # (an explicit capture stream: torch.cuda.graph otherwise reuses one process-wide default stream, which lives
+            # on the device of the FIRST capture)
+            with torch.cuda.graph(self.graph, stream=side):
                 run()
 
     def replay(self):
