@@ -88,8 +88,10 @@ class ShardedCodec:
             flat = torch.empty(sum(lens) * up, dtype=torch.float32, device=device)
             outs = list(torch.split(flat, [L * up for L in lens]))
         local, dst_views, src_views = [], [], []
-        for pad_len, jobs in sorted(groups.items()):
-            shards = windows.shard_round_robin(len(jobs), [j.n_valid for j in jobs], world)
+        order = sorted(groups.items())
+        # the groups (one launch set per pad length) are sharded jointly: a small group goes to few ranks (windows.shard_groups)
+        all_shards = windows.shard_groups([[j.n_valid for j in jobs] for _, jobs in order], world)
+        for (pad_len, jobs), shards in zip(order, all_shards):
             my_jobs = [jobs[j] for j in shards[rank]]
             if my_jobs:
                 wav = self.decode_jobs(codes_list, my_jobs, device)                         # (n_r, 1280 T')

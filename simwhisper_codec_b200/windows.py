@@ -112,15 +112,43 @@ def decode_keep(job: DecodeJob, overlap_seconds: int = 10, sr: int = 16000, max_
     return job.start * up, min(job.n_valid, keep) * up
 
 
-def shard_round_robin(n_jobs: int, cost: Sequence[int], world: int) -> List[List[int]]:
-    """Deal jobs to ranks longest-first (greedy by remaining load).  Deterministic on every rank."""
+def shard_round_robin(n_jobs: int, cost: Sequence[int], world: int, load: Sequence[int] = None,
+                      ranks: Sequence[int] = None) -> List[List[int]]:
+    """Deal jobs to ranks longest-first (greedy by remaining load).  Deterministic on every rank.
+    load: work the ranks already carry (updated in place when a list is passed); ranks: deal only to these ranks."""
     order = sorted(range(n_jobs), key=lambda j: (-cost[j], j))
-    load = [0] * world
+    load = [0] * world if load is None else load
+    ranks = list(range(world)) if ranks is None else list(ranks)
     out: List[List[int]] = [[] for _ in range(world)]
     for j in order:
-        r = min(range(world), key=lambda k: (load[k], k))
+        r = min(ranks, key=lambda k: (load[k], k))
         out[r].append(j)
         load[r] += max(cost[j], 1)
     for r in range(world):
         out[r].sort()
+    return out
+
+
+def shard_groups(group_costs: Sequence[Sequence[int]], world: int, per_job: int = 10, per_set: int = 400) -> List[List[List[int]]]:
+    """Shard several job groups that run as separate launch sets (decode windows of different pad length T') jointly:
+    a group whose whole cost is a fraction of one rank's fair share is not scattered over all ranks (every rank would pay
+    a launch set of a few windows at poor GPU efficiency) but dealt to the k least-loaded ranks, k = its cost in fair
+    shares rounded up; the larger groups then fill the ranks up.  Cost of a job = its valid code frames + per_job (the
+    Vocos halo, 80 frames = 10 code frames); a rank that takes part in a group pays per_set on top (the ~440 launches of
+    a set, measured ~1.5 ms = 400 code frames of work).  Returns, per group, the per-rank job index lists.
+    Deterministic on every rank; any split gives the same results (windows are independent)."""
+    costs = [[max(c, 0) + per_job for c in g] for g in group_costs]
+    total = sum(sum(g) for g in costs)
+    fair = max(1.0, total / max(world, 1) + per_set)
+    load = [0] * world
+    out: List[List[List[int]]] = [None] * len(costs)
+    for g in sorted(range(len(costs)), key=lambda g: (sum(costs[g]), g)):      # smallest group first
+        k = max(1, -(-sum(costs[g]) // int(fair)))
+        if 2 * k > world:                      # a group of more than half the job goes to every rank
+            k = world
+        ranks = sorted(range(world), key=lambda r: (load[r], r))[:k]
+        if costs[g]:
+            for r in ranks:
+                load[r] += per_set
+        out[g] = shard_round_robin(len(costs[g]), costs[g], world, load, ranks)
     return out

@@ -148,6 +148,25 @@ def test_shard_is_a_partition():
         assert max(sum(cost[j] for j in s) for s in sh) <= max(sum(cost) / world + max(cost), max(cost))
 
 
+def test_joint_sharding_of_decode_groups():
+    """Decode windows of different pad lengths run as separate launch sets: a small group goes to few ranks instead of
+    leaving every rank a launch set of a handful of windows, and the total load stays balanced."""
+    import random
+    rnd = random.Random(5)
+    big = [rnd.randint(25, 375) for _ in range(256)]
+    small = [rnd.randint(1, 125) for _ in range(90)]
+    for world in (1, 2, 4, 8):
+        sh = windows.shard_groups([small, big], world)
+        for costs, g in zip((small, big), sh):
+            assert len(g) == world and sorted(j for s in g for j in s) == list(range(len(costs)))
+        load = [sum(small[j] for j in sh[0][r]) + sum(big[j] for j in sh[1][r]) for r in range(world)]
+        fair = (sum(small) + sum(big)) / world
+        # (the rank that takes the small group is under-loaded on purpose: 10 frames of halo per window + one more launch set)
+        assert max(load) <= fair + 375 + 10 * len(small) + 400 and min(load) >= fair - 4 * 375
+        assert sum(1 for s in sh[0] if s) <= max(1, world // 4)                            # the small group is not scattered
+    assert windows.shard_groups([], 4) == [] and windows.shard_groups([[]], 2) == [[[], []]]
+
+
 def _worker(rank, world, port, lens, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)

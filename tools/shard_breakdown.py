@@ -47,7 +47,7 @@ def main():
         jobs = windows.plan_encode(lens, 10, m.input_sample_rate, m.max_audio_seconds)
         shards = windows.shard_round_robin(len(jobs), [j.n_valid for j in jobs], world)
         st["enc_plan"] = time.perf_counter() - t0
-        mine = m.encode_jobs(wavs, [jobs[j] for j in shards[0]], dev)
+        mine = m.encode_jobs(wavs, [jobs[j] for j in shards[int(os.environ.get('RANK_EMU', '0'))]], dev)
         st["enc_jobs_host"] = time.perf_counter() - t0
         torch.cuda.synchronize()
         st["enc_synced"] = time.perf_counter() - t0
@@ -64,9 +64,11 @@ def main():
         groups = windows.plan_decode(clens, 10, m.input_sample_rate, m.max_audio_seconds, m.encoder_downsample_rate)
         st["dec_plan"] = time.perf_counter() - t1
         n_my = 0
-        for pad_len, dj in sorted(groups.items()):
-            sh = windows.shard_round_robin(len(dj), [j.n_valid for j in dj], world)
-            my = [dj[j] for j in sh[0]]
+        order = sorted(groups.items())
+        all_sh = windows.shard_groups([[j.n_valid for j in dj] for _, dj in order], world)
+        which = int(os.environ.get("RANK_EMU", "0"))
+        for (pad_len, dj), sh in zip(order, all_sh):
+            my = [dj[j] for j in sh[which]]
             n_my += len(my)
             if my:
                 m.decode_jobs(codes_list, my, dev)
