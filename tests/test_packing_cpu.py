@@ -31,6 +31,23 @@ def test_library_exports_every_declared_symbol():
     assert lib.swc_version() >= 100
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/swc.h is the boundary a host in any language binds: it must compile as C99 (no C++ / torch types) and a
+    plain-C program must link against libswc.so and drive the model lifecycle and the error path (examples/c_abi_check.c)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "c_abi_check")
+    libdir = os.path.join(ROOT, "simwhisper_codec_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_abi_check.c"), "-o", exe, os.path.join(libdir, "libswc.so"),
+                    "-Wl,-rpath," + libdir], check=True, capture_output=True, timeout=120)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "state_dict" in r.stdout and r.stdout.strip().endswith("ok")
+
+
 def test_compute_fails_loudly_without_gpu(gen_params):
     if torch.cuda.is_available():
         pytest.skip("GPU present")
