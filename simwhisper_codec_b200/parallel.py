@@ -14,6 +14,7 @@ What travels:
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional
 
 import torch
@@ -90,40 +91,46 @@ class ShardedCodec:
         local, dst_views, src_views = [], [], []
         order = sorted(groups.items())
         # the groups (one launch set per pad length) are sharded jointly: a small group goes to few ranks (windows.shard_groups)
-        all_shards = windows.shard_groups([[j.n_valid for j in jobs] for _, jobs in order], world)
+        if os.environ.get("SWC_SHARD_JOINT", "1") != "0":
+            all_shards = windows.shard_groups([[j.n_valid for j in jobs] for _, jobs in order], world)
+        else:                                # every group dealt to every rank (A/B switch for measurements)
+            all_shards = [windows.shard_round_robin(len(jobs), [j.n_valid for j in jobs], world) for _, jobs in order]
+        # every group's launch set first, ONE gather at the end: a collective between the groups would make the ranks that
+        # have no window in a group wait (on the device) for the ranks that do
+        wavs = []
         for (pad_len, jobs), shards in zip(order, all_shards):
             my_jobs = [jobs[j] for j in shards[rank]]
-            if my_jobs:
-                wav = self.decode_jobs(codes_list, my_jobs, device)                         # (n_r, 1280 T')
-            else:
-                wav = torch.empty((0, up * pad_len), dtype=torch.float32, device=device)
+            wav = self.decode_jobs(codes_list, my_jobs, device) if my_jobs else None        # (n_r, 1280 T')
+            wavs.append(wav)
             if not gather_wav:
                 for k, j in enumerate(my_jobs):
                     off, n = windows.decode_keep(j, *keep_args)
                     local.append((j.item, off, wav[k, :n]))
-                continue
-            # only the samples that are kept travel: every rank packs the kept part of its windows into one flat buffer
+        if gather_wav:
+            # only the samples that are kept travel: every rank packs the kept part of all its windows into one flat buffer
             # (all ranks know all jobs, hence every rank's total), rank dst receives world buffers of the largest total
-            keeps = [[windows.decode_keep(jobs[j], *keep_args) for j in s] for s in shards]
-            totals = [sum(n for _, n in ks) for ks in keeps]
-            send = torch.empty(max(totals), dtype=torch.float32, device=device)
-            if my_jobs:
-                torch._foreach_copy_(list(torch.split(send[: totals[rank]], [n for _, n in keeps[rank]])),
-                                     [wav[k, :n] for k, (_, n) in enumerate(keeps[rank])])
+            keeps = [[[windows.decode_keep(jobs[j], *keep_args) for j in s] for s in shards]
+                     for (_, jobs), shards in zip(order, all_shards)]                       # [group][rank][window] -> (offset, n)
+            totals = [sum(n for g in keeps for _, n in g[r]) for r in range(world)]
+            send = torch.empty(max(totals + [1]), dtype=torch.float32, device=device)
+            mine_n = [n for g in keeps for _, n in g[rank]]
+            if mine_n:
+                torch._foreach_copy_(list(torch.split(send[: totals[rank]], mine_n)),
+                                     [wav[k, :n] for wav, g in zip(wavs, keeps) for k, (_, n) in enumerate(g[rank])])
             if world == 1:
                 bufs = [send]
             else:
                 bufs = [torch.empty_like(send) for _ in range(world)] if on_dst else None
                 dist.gather(send, bufs, dst=dist.get_global_rank(self.group, self.dst) if self.group is not None else self.dst,
                             group=self.group)
-            if not on_dst:
-                continue
-            for r, s in enumerate(shards):
-                pos = 0
-                for j, (off, n) in zip(s, keeps[r]):
-                    dst_views.append(outs[jobs[j].item][off:off + n])
-                    src_views.append(bufs[r][pos:pos + n])
-                    pos += n
+            if on_dst:
+                for r in range(world):
+                    pos = 0
+                    for ((_, jobs), shards), g in zip(zip(order, all_shards), keeps):
+                        for j, (off, n) in zip(shards[r], g[r]):
+                            dst_views.append(outs[jobs[j].item][off:off + n])
+                            src_views.append(bufs[r][pos:pos + n])
+                            pos += n
         if not gather_wav:
             return {"local": local}
         if on_dst and dst_views:
