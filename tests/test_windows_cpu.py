@@ -183,14 +183,16 @@ def _worker(rank, world, port, lens, q):
     dist.destroy_process_group()
 
 
-def test_sharded_equals_single_process_gloo():
-    lens = [48123, 800000, 365000, 1280 * 250, 479999]
+@pytest.mark.parametrize("world,lens", [(2, [48123, 800000, 365000, 1280 * 250, 479999]),
+                                        (3, [48123, 70000]),                       # a rank without any window
+                                        (3, [1000000, 2000, 330000, 481000])])     # three decode groups over three ranks
+def test_sharded_equals_single_process_gloo(world, lens):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, lens, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, lens, q)) for r in range(world)]
     for p in procs:
         p.start()
     codes2, wav2 = q.get(timeout=120)
