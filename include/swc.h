@@ -122,9 +122,13 @@ int swc_detokenize(const swc_model* m, const void* codes, int codes_are_int64, c
 
 /* ---- the same two chains when the caller also knows the lengths on the HOST (AudioCodec.encode()/decode() do:
  *      model.py:262-268, 327-333 build them from Python lists).  In bf16 mode the two transformer stacks then run on the
- *      packed valid tokens only (padded tokens of a window are skipped); results are bit-identical to swc_tokenize /
- *      swc_detokenize.  host_lengths[b] must equal lengths[b]; a call takes at most swc_max_ragged() items (the length table
- *      travels as a kernel parameter): larger batches are an error, the caller splits them (AudioCodec does). ---- */
+ *      packed valid tokens only (padded tokens of a window are skipped), and swc_detokenize_ragged runs Vocos only over
+ *      each item's valid frames plus its receptive-field halo, all items packed into one batch of rows.  Codes, code lengths
+ *      and the first out_lens[b] = 1280 lens[b] samples of every item are bit-identical to swc_tokenize / swc_detokenize;
+ *      samples of wav beyond an item's out_lens[b] are NOT written by the ragged form (the padded form computes them from
+ *      the padding, as the reference does; its callers discard them: model.py:352-356).  host_lengths[b] must equal
+ *      lengths[b]; a call takes at most swc_max_ragged() items (the length tables travel as kernel parameters): larger
+ *      batches are an error, the caller splits them (AudioCodec does). ---- */
 int swc_max_ragged(void);
 int swc_tokenize_ragged(const swc_model* m, const float* wav, int64_t wav_stride, int wav_cols, const int64_t* lengths,
                         const int64_t* host_lengths, int batch, int32_t* codes, float* zq_cf, int64_t* codes_lens,
