@@ -139,3 +139,25 @@ def test_outlier_weights_forward(gen_params):
     assert float(flips) < 1e-3, float(flips)
     rms = g["channel_rms"]
     assert rms[list(W.OUTLIER_CHANNELS)].min() > 20 * np.median(rms)      # the stress is what it says: >20x outlier channels
+
+
+def test_vocos_receptive_field_bounds_the_packed_form(sd_ex):
+    """decode() with host-known lengths computes only need = min(Tv, 8 len + 80) Vocos frames per window and treats the cut
+    as a sequence end (pipeline.cu::detokenize_chain).  In the reference arithmetic (float64 here) the first 1280 len samples of
+    a window must then not depend on what lies beyond the cut: 3 frames per depthwise convolution and for the embedding
+    (25 x 3 = 75) + 1 for the overlap-add = 76 < 80.  A halo of 4 frames must NOT be enough (the cut does reach valid samples
+    when it sits too close; with these weights the influence decays by ~10^3 per 8 frames)."""
+    sd = port.cast_sd(sd_ex, torch.float64)
+    g = torch.Generator().manual_seed(11)
+    Tv = 232
+    x = torch.randn(1, 80, Tv, generator=g, dtype=torch.float64)
+    with torch.inference_mode():
+        full = port.vocos(sd, x, torch.tensor([Tv]))[0][0, 0]
+        for code_len in (1, 9, 18):
+            need = min(Tv, 8 * code_len + 80)
+            cut = port.vocos(sd, x[:, :, :need].contiguous(), torch.tensor([need]))[0][0, 0]
+            n = 1280 * code_len
+            assert (cut[:n] - full[:n]).abs().max().item() <= 1e-10 * full.abs().max().item(), code_len
+        short = port.vocos(sd, x[:, :, : 8 * 9 + 4].contiguous(), torch.tensor([8 * 9 + 4]))[0][0, 0]
+        assert (short[: 1280 * 9] - full[: 1280 * 9]).abs().max().item() > 1e-3 * full.abs().max().item()
+
